@@ -1,0 +1,191 @@
+/* mfvae.h — C ABI of the B200-native MF-VAE (class MAVAE) training hot path.
+ *
+ * Drop-in boundary for the reference path /root/reference/torch_ver:
+ *   model.py:134-173   MAVAE.forward          -> mfvae_forward
+ *   model.py:19-40     loss_s_r_vae_fn        -> mfvae_loss       (forward value + d loss / d recon)
+ *   model.py:8-16      loss_vae_fn            -> mfvae_loss with joint_mse = 1
+ *   main.py:92-93 / trainer.py:98-100  zero_grad + loss.backward() -> mfvae_backward
+ *   main.py:97   / trainer.py:102-103  torch.optim.Adam.step()     -> mfvae_adam_step
+ *   trainer.py:7-45    create_dataset (host numpy) -> mfvae_stage (device gather from packed rows)
+ *   src/replay_buffer.py:53-115 (cpprb, C++) / jax_ver/jax_buffer.py:80-140 (flashbax)
+ *                                             -> mfvae_ring_* (HBM-resident ring + gather)
+ *
+ * Conventions: every entry point returns 0 on success, non-zero on failure;
+ * mfvae_last_error() returns a thread-local message.  No exceptions or aborts cross the ABI.
+ * All pointers named d_* are device pointers owned by the caller (the Python host allocates them as
+ * torch tensors); the library never frees caller memory.  `stream` is a cudaStream_t passed as void*.
+ * A handle is not thread-safe (one per rank / thread), matching the reference's single-threaded use.
+ */
+#ifndef MFVAE_H_
+#define MFVAE_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFVAE_MAX_HIDDEN 8
+
+enum { MFVAE_PREC_FP32 = 0, MFVAE_PREC_BF16 = 1 };
+/* GEMM engines.  AUTO = tcgen05 for bf16, SIMT FFMA for fp32.  SIMT with bf16 is a debugging aid that
+ * runs the same data flow without tensor cores; it is NOT a fallback: nothing selects it implicitly. */
+enum { MFVAE_ENGINE_AUTO = 0, MFVAE_ENGINE_SIMT = 1, MFVAE_ENGINE_TCGEN05 = 2 };
+enum { MFVAE_LOSS_DEFAULT = 0, MFVAE_LOSS_HUBER = 1, MFVAE_LOSS_MSE = 2, MFVAE_LOSS_JOINT_MSE = 3 };
+
+typedef struct MfvaeConfig {
+  int32_t n_agents;                      /* A                                   model.py:116 */
+  int32_t idx_features;                  /* I  (IDX_FEATURES, main.py:30)                    */
+  int32_t latent;                        /* L  (OBS_FEATURES, main.py:31)                    */
+  int32_t act_features;                  /* C  (ACT_FEATURES, main.py:32)                    */
+  int32_t n_enc_hidden;                  /* Encoder.HIDDEN  model.py:46 -> {64,64,256}       */
+  int32_t enc_hidden[MFVAE_MAX_HIDDEN];
+  int32_t n_dec_hidden;                  /* Decoder.HIDDEN  model.py:87 -> {1024,256,64,256,1024} */
+  int32_t dec_hidden[MFVAE_MAX_HIDDEN];
+  const int32_t* obs_dim;                /* [A] host, observation width per agent            */
+  const int32_t* n_act;                  /* [A] host, #discrete actions per agent            */
+  float kl_weight;                       /* model.py:5                                       */
+  float r_weight;                        /* model.py:6                                       */
+  int32_t huber;                         /* 1: Huber(delta=1) (model.py:25-31), 0: MSE       */
+  int32_t precision;                     /* MFVAE_PREC_*                                     */
+  int32_t engine;                        /* MFVAE_ENGINE_*                                   */
+  int32_t optimize_encoders;             /* 0 = reference semantics: encoders / action tables get
+                                            gradients but no Adam update (model.py:112,114)  */
+} MfvaeConfig;
+
+/* One tensor of the parameter arena.  Offsets are in ELEMENTS and identical for the fp32 master,
+ * gradient, Adam m / v and bf16 shadow arenas.  A tensor is rows x cols with row stride ld
+ * (ld >= cols; padding columns are kept at zero). */
+enum { MFVAE_T_IDX_EMB = 0, MFVAE_T_ENC_W, MFVAE_T_ENC_B, MFVAE_T_ACT_TABLE,
+       MFVAE_T_SDEC_W, MFVAE_T_SDEC_B, MFVAE_T_RDEC_W, MFVAE_T_RDEC_B,
+       MFVAE_T_RLIN_W, MFVAE_T_RLIN_B };
+typedef struct MfvaeTensorInfo {
+  int32_t kind;      /* MFVAE_T_*                         */
+  int32_t agent;     /* agent index or -1                 */
+  int32_t layer;     /* Linear index inside its MLP or -1 */
+  int32_t rows, cols, ld;
+  int64_t offset;
+} MfvaeTensorInfo;
+
+typedef struct MfvaeArenas {
+  float* d_param;          /* fp32 master weights                       */
+  float* d_grad;           /* fp32 gradients                            */
+  float* d_m;              /* Adam exp_avg                              */
+  float* d_v;              /* Adam exp_avg_sq                           */
+  void*  d_shadow_bf16;    /* bf16 copy the tensor-core GEMMs read (may be NULL for fp32) */
+} MfvaeArenas;
+
+/* Packed device batch (what create_dataset builds on the host in the reference, trainer.py:7-45):
+ * obs/next are the agents' observation vectors concatenated in codebook order. */
+typedef struct MfvaeBatch {
+  const float* d_obs;      /* [B, S]   fp32                                            */
+  const float* d_act;      /* [B, A]   fp32-coded action index (replay_buffer.py:76)   */
+  const float* d_next;     /* [B, S]   target next state   (may be NULL for forward only) */
+  const float* d_rew;      /* [B, A]   target rewards      (may be NULL for forward only) */
+  const float* d_idx;      /* [B, A]   fp32-coded agent index column, or NULL = codebook order */
+  const float* d_eps;      /* [B, A*L] explicit eps, or NULL = Philox(seed, step, sample)      */
+  int32_t batch;           /* B on this rank                                            */
+  int64_t sample0;         /* global index of row 0 (Philox counter; rank * B for DP)   */
+  int64_t batch_global;    /* B summed over ranks: the loss means divide by this        */
+  uint64_t seed;           /* Philox key                                                */
+  uint64_t step;           /* Philox counter word 3                                     */
+} MfvaeBatch;
+
+typedef struct MfvaeOutputs {
+  const float* d_recon_s;  int32_t recon_s_ld;   /* [B, S]  fp32 (model.py:169)          */
+  const float* d_recon_r;  int32_t recon_r_ld;   /* [B, A]  fp32 (model.py:170)          */
+  const float* d_latent;                          /* [A][B][2L] fp32: cols [0,L)=mu, [L,2L)=logvar (model.py:149-150) */
+  const float* d_losses;                          /* [4] loss, s_loss, r_loss, kl_loss (model.py:40); partial
+                                                     (this rank's share of the global means) until all-reduced */
+} MfvaeOutputs;
+
+typedef struct MfvaeHandle_* MfvaeHandle;
+
+const char* mfvae_last_error(void);
+int mfvae_version(void);
+
+/* lifecycle.  device = -1 makes a layout-only handle (arena / tensor table queries work, every compute
+ * call fails): used by host-side tests on machines without a GPU. */
+int mfvae_create(const MfvaeConfig* cfg, int device, MfvaeHandle* out);
+int mfvae_destroy(MfvaeHandle h);
+
+/* parameter arena description */
+int64_t mfvae_arena_elems(MfvaeHandle h);                 /* total elements (multiple of 8)          */
+int64_t mfvae_optimized_elems(MfvaeHandle h);             /* prefix [0, n) that Adam updates          */
+int32_t mfvae_tensor_count(MfvaeHandle h);
+int mfvae_tensor_table(MfvaeHandle h, MfvaeTensorInfo* out, int32_t capacity);
+int mfvae_bind_arenas(MfvaeHandle h, const MfvaeArenas* arenas);
+int mfvae_refresh_shadow(MfvaeHandle h, void* stream);    /* fp32 master -> bf16 shadow (whole arena) */
+
+/* activation workspace: caller allocates mfvae_workspace_bytes(h, B) bytes (256-B aligned) */
+int64_t mfvae_workspace_bytes(MfvaeHandle h, int32_t batch);
+int mfvae_bind_workspace(MfvaeHandle h, void* d_ws, int64_t bytes, int32_t batch);
+
+/* the train step, piecewise (reference call sites in the file header) */
+int mfvae_forward(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* stream);
+/* loss_kind: MFVAE_LOSS_DEFAULT (cfg.huber), _HUBER / _MSE (loss_s_r_vae_fn, model.py:19-40) or
+ * _JOINT_MSE (loss_vae_fn, model.py:8-16) */
+int mfvae_loss(MfvaeHandle h, const MfvaeBatch* b, int32_t loss_kind, void* stream);
+/* the reference reads kl_weight / r_weight module globals at call time (model.py:5-6,34,39) */
+int mfvae_set_loss_weights(MfvaeHandle h, float kl_weight, float r_weight);
+int mfvae_backward(MfvaeHandle h, const MfvaeBatch* b, void* stream);
+/* backward seeded by caller-provided upstream gradients (autograd bridge for losses other than the fused
+ * ELBO): d loss / d recon_s [B, ld_s], d loss / d recon_r [B, ld_r], d loss / d latent [A][B][2L]; fp32, any
+ * of them may be NULL (= zero).  The analytic KL term is NOT added (it is part of the caller's loss). */
+int mfvae_backward_ext(MfvaeHandle h, const MfvaeBatch* b, const float* d_g_recon_s, int64_t ld_s,
+                       const float* d_g_recon_r, int64_t ld_r, const float* d_g_latent, void* stream);
+int mfvae_adam_step(MfvaeHandle h, float lr, float beta1, float beta2, float eps, int64_t t, void* stream);
+/* forward + loss + backward in one call (no optimizer; the host all-reduces gradients in between) */
+int mfvae_fwd_bwd(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* stream);
+
+/* gradient buckets in backward-completion order, for the overlapped all-reduce: bucket i covers
+ * arena elements [begin, end) and is final once event i (cudaEvent_t, returned as void*) fires. */
+int32_t mfvae_bucket_count(MfvaeHandle h);
+int mfvae_bucket(MfvaeHandle h, int32_t i, int64_t* begin, int64_t* end, void** event);
+/* make `stream` (e.g. the NCCL stream) wait for bucket i's event */
+int mfvae_bucket_wait(MfvaeHandle h, int32_t i, void* stream);
+
+/* standalone bandwidth-bound kernels (BASELINE config 5 microbenchmarks; also used by the step).
+ * dtype: 0 = fp32 activations, 1 = bf16 activations (mu / logvar / recon / target stay fp32). */
+int mfvae_reparam_kl(const float* d_mu, const float* d_logvar, const float* d_eps_or_null,
+                     void* d_z, int32_t z_dtype, int64_t batch, int32_t width /* A*L */,
+                     uint64_t seed, uint64_t step, int64_t sample0, int64_t batch_global,
+                     float* d_kl_out /* [1] */, float* d_scratch /* >= 4096 floats */, void* stream);
+int mfvae_recon_loss(const float* d_recon, int32_t recon_ld, const float* d_target, int32_t target_ld,
+                     void* d_grad, int32_t grad_ld, int32_t grad_dtype, int64_t batch, int32_t width,
+                     int32_t huber, float weight, int64_t count_global,
+                     float* d_loss_out /* [1] */, float* d_scratch /* >= 4096 floats */, void* stream);
+int mfvae_adam_flat(float* d_p, const float* d_g, float* d_m, float* d_v, void* d_shadow_bf16_or_null,
+                    int64_t n, float lr, float beta1, float beta2, float eps, int64_t t, void* stream);
+int mfvae_philox_normal(float* d_out, int64_t batch, int32_t width, uint64_t seed, uint64_t step,
+                        int64_t sample0, void* stream);
+
+/* generic GEMM entry (tests + microbench): C[M,N] (+)= A[M,K] * B[N,K]^T with element strides.
+ * dtype 0 fp32 / 1 bf16 operands; C fp32 when c_dtype = 0 else bf16.  engine: MFVAE_ENGINE_*.
+ * epilogue: 0 none, 1 +bias, 2 +bias,relu, 3 multiply by (aux > 0), 4 accumulate into fp32 C. */
+int mfvae_gemm(int32_t engine, int32_t dtype, int32_t groups, int32_t M, int32_t N, int32_t K,
+               const void* d_A, int64_t a_gs, int64_t a_rs, int64_t a_cs,
+               const void* d_B, int64_t b_gs, int64_t b_rs, int64_t b_cs,
+               void* d_C, int64_t c_gs, int64_t c_ld, int32_t c_dtype,
+               const float* d_bias, int64_t bias_gs, int32_t epilogue,
+               const void* d_aux, int64_t aux_gs, int64_t aux_ld, int32_t split_k, void* stream);
+
+/* HBM-resident replay ring (replaces cpprb.ReplayBuffer / flashbax item buffer on this path).
+ * Row = one joint transition: [obs(S) | act(A) | next(S) | rew(A) | done(1)] fp32. */
+typedef struct MfvaeRing_* MfvaeRing;
+int mfvae_ring_create(int32_t state_dim, int32_t n_agents, int64_t capacity, float* d_storage, MfvaeRing* out);
+int mfvae_ring_destroy(MfvaeRing r);
+int64_t mfvae_ring_row_floats(int32_t state_dim, int32_t n_agents);
+int64_t mfvae_ring_size(MfvaeRing r);
+/* append n rows from a host or device staging buffer (cudaMemcpyAsync, wraps around) */
+int mfvae_ring_add(MfvaeRing r, const float* rows, int64_t n, int32_t rows_on_device, void* stream);
+/* uniform-with-replacement sample (Philox(seed, step)) and gather into the packed batch matrices */
+int mfvae_ring_sample(MfvaeRing r, int64_t batch, uint64_t seed, uint64_t step,
+                      float* d_obs, float* d_act, float* d_next, float* d_rew, int32_t* d_indices_or_null,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFVAE_H_ */

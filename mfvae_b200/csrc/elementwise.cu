@@ -1,0 +1,524 @@
+// elementwise.cu — the HBM-bound kernels of the MAVAE train step (sm_100a).
+//
+//   stage            trainer.py:7-45 (create_dataset) + model.py:142-146 (id / action embedding gathers)
+//   reparam_kl_fwd   model.py:77-81 (reparameterize) + model.py:35-37 (analytic Gaussian KL)
+//   recon_loss       model.py:25-34 (Huber / MSE mean) forward value and d/d recon in one pass
+//   reparam_kl_bwd   closed-form backward of the two above w.r.t. (mu, logvar)
+//   colsum           bias gradients
+//   adam             torch.optim.Adam single-pass fused update (+ bf16 shadow write)
+//
+// All of them move each byte once: 128-bit global accesses, grid sized to a multiple of the 148 SMs,
+// grid-stride loops, warp-shuffle -> shared -> one partial per CTA, and a last-CTA-done ticket so the
+// final scalar is produced in the same launch in a fixed (deterministic) order.
+#include <algorithm>
+
+#include "kernels.h"
+
+namespace mfvae {
+
+constexpr int kThreads = 256;
+constexpr int kMaxPartials = 2048;          // scratch[0..2047] partials, scratch[4095] ticket
+constexpr int kTicketSlot = 4095;
+
+static inline int grid_for(int64_t work_items, int per_sm = 8) {
+  int64_t blocks = (work_items + kThreads - 1) / kThreads;
+  int64_t cap = static_cast<int64_t>(kNumSMs) * per_sm;     // multiple of the SM count
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+// Sum per-CTA partials in a fixed order once every CTA has published; the last CTA to take a ticket
+// does it, then re-arms the ticket for the next launch.
+__device__ __forceinline__ void finish_scalar(float block_total, float* scratch, float scale, float* out,
+                                              float* red) {
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+    scratch[blockIdx.x] = block_total;
+    __threadfence();
+    unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(scratch + kTicketSlot), 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float v = 0.f;
+    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += blockDim.x) v += __ldcg(scratch + i);
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) {
+      out[0] = v * scale;
+      *reinterpret_cast<unsigned int*>(scratch + kTicketSlot) = 0u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage: packed fp32 rows -> encoder input X0[a][b][:] = [idx_emb[id] | obs_a | 0] and the action-embedding
+// half of the decoder input.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) stage_kernel(StageArgs p) {
+  const int nvec = p.x0_ld / 4;
+  const int64_t per_agent = static_cast<int64_t>(p.B) * nvec;
+  const int64_t total = per_agent * p.A;
+  T* x0 = static_cast<T*>(p.x0);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int a = static_cast<int>(i / per_agent);
+    const int64_t r = i - a * per_agent;
+    const int b = static_cast<int>(r / nvec);
+    const int c0 = static_cast<int>(r - static_cast<int64_t>(b) * nvec) * 4;
+    const int od = p.obs_dim[a], off = p.obs_off[a];
+    int id = a;
+    if (p.idx) id = static_cast<int>(p.idx[static_cast<int64_t>(b) * p.A + a]);
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + k;
+      float x = 0.f;
+      if (c < p.I) x = p.idx_emb[static_cast<int64_t>(id) * p.I + c];
+      else if (c < p.I + od) x = __ldg(p.obs + static_cast<int64_t>(b) * p.obs_ld + off + (c - p.I));
+      v[k] = x;
+    }
+    store4<T>(x0 + a * p.x0_gs + static_cast<int64_t>(b) * p.x0_ld + c0, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) act_embed_kernel(StageArgs p) {
+  const int cvec = p.C / 4;
+  const int64_t total = static_cast<int64_t>(p.B) * p.A * cvec;
+  T* zin = static_cast<T*>(p.zin);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cq = static_cast<int>(i % cvec);
+    const int64_t r = i / cvec;
+    const int a = static_cast<int>(r % p.A);
+    const int64_t b = r / p.A;
+    int act = static_cast<int>(p.act[b * p.act_ld + a]);
+    act = max(0, min(act, p.n_act[a] - 1));
+    const float4 e = *reinterpret_cast<const float4*>(p.act_table + a * p.act_table_gs +
+                                                     static_cast<int64_t>(act) * p.C + cq * 4);
+    store4<T>(zin + b * p.zin_ld + p.A * p.L + a * p.C + cq * 4, e);
+  }
+}
+
+int launch_stage(const StageArgs& a, cudaStream_t s) {
+  MFVAE_CHECK(a.x0_ld % 4 == 0 && a.C % 4 == 0 && a.zin_ld % 4 == 0, "stage: widths must be multiples of 4");
+  const int64_t t0 = static_cast<int64_t>(a.A) * a.B * (a.x0_ld / 4);
+  const int64_t t1 = static_cast<int64_t>(a.A) * a.B * (a.C / 4);
+  if (a.dtype == kBF16) {
+    stage_kernel<__nv_bfloat16><<<grid_for(t0), kThreads, 0, s>>>(a);
+    act_embed_kernel<__nv_bfloat16><<<grid_for(t1), kThreads, 0, s>>>(a);
+  } else {
+    stage_kernel<float><<<grid_for(t0), kThreads, 0, s>>>(a);
+    act_embed_kernel<float><<<grid_for(t1), kThreads, 0, s>>>(a);
+  }
+  MFVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reparameterize + KL.  One thread = 4 consecutive latent columns of one (sample, agent):
+// 2 x 16-B loads (mu, logvar), one Philox4x32-10 call = 4 normals, one 16-B (fp32) / 8-B (bf16) store.
+// Algorithmic bytes per sample: 3 * A*L * 4 (fp32 z) = SURVEY 8(d).
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool AGENT_MAJOR>
+__global__ void __launch_bounds__(kThreads) reparam_kl_fwd_kernel(ReparamArgs p) {
+  __shared__ float red[32];
+  const int lq = p.L / 4;
+  const int64_t total = p.B * p.A * lq;
+  T* z = static_cast<T*>(p.z);
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int jq = static_cast<int>(i % lq);
+    const int64_t r = i / lq;
+    int a; int64_t b;
+    if (AGENT_MAJOR) { b = r % p.B; a = static_cast<int>(r / p.B); }
+    else             { a = static_cast<int>(r % p.A); b = r / p.A; }
+    const int64_t off = a * p.lat_as + b * p.lat_bs + jq * 4;
+    const float4 mu = ldg_stream4(p.mu + off);
+    const float4 lv = ldg_stream4(p.lv + off);
+    const int col = a * p.L + jq * 4;
+    float4 e;
+    if (p.eps) e = ldg_stream4(p.eps + b * p.eps_ld + col);
+    else       e = philox_normal4(p.seed, p.step, static_cast<uint64_t>(p.sample0 + b), static_cast<uint32_t>(col >> 2));
+    float4 o;
+    const float ex = expf(lv.x), ey = expf(lv.y), ez = expf(lv.z), ew = expf(lv.w);
+    o.x = mu.x + e.x * expf(0.5f * lv.x);
+    o.y = mu.y + e.y * expf(0.5f * lv.y);
+    o.z = mu.z + e.z * expf(0.5f * lv.z);
+    o.w = mu.w + e.w * expf(0.5f * lv.w);
+    store4<T>(z + b * p.z_ld + col, o);
+    acc += (1.f + lv.x - mu.x * mu.x - ex) + (1.f + lv.y - mu.y * mu.y - ey) +
+           (1.f + lv.z - mu.z * mu.z - ez) + (1.f + lv.w - mu.w * mu.w - ew);
+  }
+  const float tot = block_sum(acc, red);
+  finish_scalar(tot, p.scratch, -0.5f * p.kl_scale, p.kl_out, red);
+}
+
+int launch_reparam_kl_fwd(const ReparamArgs& a, cudaStream_t s) {
+  MFVAE_CHECK(a.L % 4 == 0, "reparam: latent must be a multiple of 4");
+  MFVAE_CHECK(a.lat_as % 4 == 0 && a.lat_bs % 4 == 0 && a.z_ld % 4 == 0, "reparam: strides must be multiples of 4");
+  const int64_t total = a.B * a.A * (a.L / 4);
+  const int grid = grid_for(total);
+  const bool am = a.lat_as > a.lat_bs;
+  if (a.z_dtype == kBF16) {
+    if (am) reparam_kl_fwd_kernel<__nv_bfloat16, true><<<grid, kThreads, 0, s>>>(a);
+    else    reparam_kl_fwd_kernel<__nv_bfloat16, false><<<grid, kThreads, 0, s>>>(a);
+  } else {
+    if (am) reparam_kl_fwd_kernel<float, true><<<grid, kThreads, 0, s>>>(a);
+    else    reparam_kl_fwd_kernel<float, false><<<grid, kThreads, 0, s>>>(a);
+  }
+  MFVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename TG, typename TD>
+__global__ void __launch_bounds__(kThreads) reparam_kl_bwd_kernel(ReparamBwdArgs p) {
+  const int lq = p.L / 4;
+  const int64_t total = p.B * p.A * lq;
+  const TG* gz = static_cast<const TG*>(p.gz);
+  TD* dl = static_cast<TD*>(p.dlat);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int jq = static_cast<int>(i % lq);
+    const int64_t r = i / lq;
+    const int64_t b = r % p.B;
+    const int a = static_cast<int>(r / p.B);
+    const int64_t off = a * p.lat_as + b * p.lat_bs + jq * 4;
+    const float4 mu = *reinterpret_cast<const float4*>(p.mu + off);
+    const float4 lv = *reinterpret_cast<const float4*>(p.lv + off);
+    const int col = a * p.L + jq * 4;
+    const float4 g = load4<TG>(gz + b * p.gz_ld + col);
+    float4 e;
+    if (p.eps) e = *reinterpret_cast<const float4*>(p.eps + b * p.eps_ld + col);
+    else       e = philox_normal4(p.seed, p.step, static_cast<uint64_t>(p.sample0 + b), static_cast<uint32_t>(col >> 2));
+    const float k = p.kl_scale;
+    float4 dmu, dlv;
+    dmu.x = g.x + k * mu.x; dmu.y = g.y + k * mu.y; dmu.z = g.z + k * mu.z; dmu.w = g.w + k * mu.w;
+    dlv.x = g.x * e.x * 0.5f * expf(0.5f * lv.x) + k * 0.5f * (expf(lv.x) - 1.f);
+    dlv.y = g.y * e.y * 0.5f * expf(0.5f * lv.y) + k * 0.5f * (expf(lv.y) - 1.f);
+    dlv.z = g.z * e.z * 0.5f * expf(0.5f * lv.z) + k * 0.5f * (expf(lv.z) - 1.f);
+    dlv.w = g.w * e.w * 0.5f * expf(0.5f * lv.w) + k * 0.5f * (expf(lv.w) - 1.f);
+    if (p.glat) {
+      const float4 um = *reinterpret_cast<const float4*>(p.glat + off);
+      const float4 ul = *reinterpret_cast<const float4*>(p.glat + off + p.L);
+      dmu.x += um.x; dmu.y += um.y; dmu.z += um.z; dmu.w += um.w;
+      dlv.x += ul.x; dlv.y += ul.y; dlv.z += ul.z; dlv.w += ul.w;
+    }
+    TD* o = dl + a * p.dlat_as + b * p.dlat_bs + jq * 4;
+    store4<TD>(o, dmu);
+    store4<TD>(o + p.L, dlv);
+  }
+}
+
+int launch_reparam_kl_bwd(const ReparamBwdArgs& a, cudaStream_t s) {
+  MFVAE_CHECK(a.L % 4 == 0 && a.gz_ld % 4 == 0 && a.dlat_bs % 4 == 0, "reparam bwd: widths must be multiples of 4");
+  MFVAE_CHECK(a.g_dtype == a.d_dtype, "reparam bwd: mixed dtypes unsupported");
+  const int grid = grid_for(a.B * a.A * (a.L / 4));
+  if (a.g_dtype == kBF16) reparam_kl_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kThreads, 0, s>>>(a);
+  else                    reparam_kl_bwd_kernel<float, float><<<grid, kThreads, 0, s>>>(a);
+  MFVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reconstruction loss, forward value + gradient in one pass.
+// Reference argument order F.huber_loss(target_data, recon) is symmetric in its two arguments.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void recon_elem(float r, float t, int huber, float gs, float& val, float& g) {
+  const float d = r - t;
+  if (huber) {
+    const float ad = fabsf(d);
+    val = ad < 1.f ? 0.5f * d * d : ad - 0.5f;
+    g = fminf(fmaxf(d, -1.f), 1.f) * gs;
+  } else {
+    val = d * d;
+    g = 2.f * d * gs;
+  }
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kThreads) recon_loss_kernel(ReconLossArgs p) {
+  __shared__ float red[32];
+  T* grad = static_cast<T*>(p.grad);
+  float acc = 0.f;
+  if (VEC) {
+    const int wq = p.width / 4;
+    const int64_t total = p.B * wq;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int64_t b = i / wq;
+      const int c = static_cast<int>(i - b * wq) * 4;
+      const float4 r = ldg_stream4(p.recon + b * p.recon_ld + c);
+      const float4 t = ldg_stream4(p.target + b * p.target_ld + c);
+      float4 g; float v0, v1, v2, v3;
+      recon_elem(r.x, t.x, p.huber, p.grad_scale, v0, g.x);
+      recon_elem(r.y, t.y, p.huber, p.grad_scale, v1, g.y);
+      recon_elem(r.z, t.z, p.huber, p.grad_scale, v2, g.z);
+      recon_elem(r.w, t.w, p.huber, p.grad_scale, v3, g.w);
+      acc += (v0 + v1) + (v2 + v3);
+      if (grad) store4<T>(grad + b * p.grad_ld + c, g);
+    }
+  } else {
+    const int64_t total = p.B * p.width;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int64_t b = i / p.width;
+      const int c = static_cast<int>(i - b * p.width);
+      float v, g;
+      recon_elem(p.recon[b * p.recon_ld + c], p.target[b * p.target_ld + c], p.huber, p.grad_scale, v, g);
+      acc += v;
+      if (grad) grad[b * p.grad_ld + c] = from_f<T>(g);
+    }
+  }
+  const float tot = block_sum(acc, red);
+  finish_scalar(tot, p.scratch, p.loss_scale, p.loss_out, red);
+}
+
+int launch_recon_loss(const ReconLossArgs& a, cudaStream_t s) {
+  const bool vec = a.width % 4 == 0 && a.recon_ld % 4 == 0 && a.target_ld % 4 == 0 && a.grad_ld % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(a.recon) % 16 == 0) && (reinterpret_cast<uintptr_t>(a.target) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(a.grad) % 16 == 0);
+  const int64_t items = vec ? a.B * (a.width / 4) : a.B * a.width;
+  const int grid = grid_for(items);
+  if (a.grad_dtype == kBF16) {
+    if (vec) recon_loss_kernel<__nv_bfloat16, true><<<grid, kThreads, 0, s>>>(a);
+    else     recon_loss_kernel<__nv_bfloat16, false><<<grid, kThreads, 0, s>>>(a);
+  } else {
+    if (vec) recon_loss_kernel<float, true><<<grid, kThreads, 0, s>>>(a);
+    else     recon_loss_kernel<float, false><<<grid, kThreads, 0, s>>>(a);
+  }
+  MFVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// column sums (bias gradients): out[g][n] += sum_b X[g][b][n]
+// block = 32 (column pairs) x 8 (row phases); grid = (col tiles, row splits, groups)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int64_t B, int N, int64_t ld,
+                                                     int64_t gs, float* __restrict__ out, int64_t out_gs) {
+  __shared__ float sm[8][64];
+  const int g = blockIdx.z;
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
+  const T* xg = x + g * gs;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < N) {
+    const bool two = (c + 1 < N);
+    for (int64_t b = blockIdx.y * 8 + threadIdx.y; b < B; b += static_cast<int64_t>(gridDim.y) * 8) {
+      const T* row = xg + b * ld + c;
+      s0 += to_f<T>(row[0]);
+      if (two) s1 += to_f<T>(row[1]);
+    }
+  }
+  sm[threadIdx.y][threadIdx.x * 2] = s0;
+  sm[threadIdx.y][threadIdx.x * 2 + 1] = s1;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { s0 += sm[k][threadIdx.x * 2]; s1 += sm[k][threadIdx.x * 2 + 1]; }
+    if (c < N) atomicAdd(out + g * out_gs + c, s0);
+    if (c + 1 < N) atomicAdd(out + g * out_gs + c + 1, s1);
+  }
+}
+
+int launch_colsum(const void* x, int dtype, int G, int64_t B, int N, int64_t ld, int64_t gs,
+                  float* out, int64_t out_gs, cudaStream_t s) {
+  const int ctiles = (N + 63) / 64;
+  int64_t want = (static_cast<int64_t>(kNumSMs) * 4) / (static_cast<int64_t>(ctiles) * G);
+  int splits = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, (B + 63) / 64)));
+  dim3 grid(ctiles, splits, G), block(32, 8);
+  if (dtype == kBF16)
+    colsum_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(static_cast<const __nv_bfloat16*>(x), B, N, ld, gs, out, out_gs);
+  else
+    colsum_kernel<float><<<grid, block, 0, s>>>(static_cast<const float*>(x), B, N, ld, gs, out, out_gs);
+  MFVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// embedding gradients (scatter-add; tables are tiny, rows are many -> shared-memory pre-reduction)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) idx_emb_scatter_kernel(const T* __restrict__ gx0, int64_t gs, int64_t ld,
+                                                                   const float* __restrict__ idx, int idx_ld, int A, int I,
+                                                                   int64_t B, float* __restrict__ d_emb) {
+  const int64_t total = static_cast<int64_t>(A) * B * I;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % I);
+    const int64_t r = i / I;
+    const int64_t b = r % B;
+    const int a = static_cast<int>(r / B);
+    int id = static_cast<int>(idx[b * idx_ld + a]);
+    id = max(0, min(id, A - 1));
+    atomicAdd(d_emb + static_cast<int64_t>(id) * I + c, to_f<T>(gx0[a * gs + b * ld + c]));
+  }
+}
+
+int launch_idx_emb_scatter(const void* gx0, int dtype, int64_t gs, int64_t ld, const float* idx, int idx_ld,
+                           int A, int I, int64_t B, float* d_emb, cudaStream_t s) {
+  const int grid = grid_for(static_cast<int64_t>(A) * B * I);
+  if (dtype == kBF16)
+    idx_emb_scatter_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(gx0), gs, ld, idx, idx_ld, A, I, B, d_emb);
+  else
+    idx_emb_scatter_kernel<float><<<grid, kThreads, 0, s>>>(static_cast<const float*>(gx0), gs, ld, idx, idx_ld, A, I, B, d_emb);
+  MFVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// grid = (row chunks, A); each CTA reduces its rows into smem[n_act][C] and flushes with atomics.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) act_table_grad_kernel(const T* __restrict__ gzin, int64_t ld, int col0,
+                                                                  const float* __restrict__ act, int act_ld,
+                                                                  const int32_t* __restrict__ n_act, int C, int64_t B,
+                                                                  float* __restrict__ d_table, int64_t table_gs) {
+  extern __shared__ float acc[];
+  const int a = blockIdx.y;
+  const int na = n_act[a];
+  for (int i = threadIdx.x; i < na * C; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int rows_per_iter = blockDim.x / C > 0 ? blockDim.x / C : 1;
+  const int c = threadIdx.x % C;
+  const int rphase = threadIdx.x / C;
+  if (rphase < rows_per_iter) {
+    for (int64_t b = static_cast<int64_t>(blockIdx.x) * rows_per_iter + rphase; b < B;
+         b += static_cast<int64_t>(gridDim.x) * rows_per_iter) {
+      int k = static_cast<int>(act[b * act_ld + a]);
+      k = max(0, min(k, na - 1));
+      atomicAdd(acc + k * C + c, to_f<T>(gzin[b * ld + col0 + a * C + c]));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < na * C; i += blockDim.x) atomicAdd(d_table + a * table_gs + i, acc[i]);
+}
+
+int launch_act_table_grad(const void* gzin, int dtype, int64_t ld, int col0, const float* act, int act_ld,
+                          const int32_t* n_act, int A, int C, int64_t B, float* d_table, int64_t table_gs,
+                          cudaStream_t s) {
+  MFVAE_CHECK(C <= kThreads, "act_table_grad: act_features must be <= 256");
+  MFVAE_CHECK(table_gs * sizeof(float) <= 48 * 1024, "act_table_grad: action table too large for the shared-memory path");
+  const int rows_per_iter = kThreads / C;
+  int chunks = static_cast<int>(std::min<int64_t>((B + rows_per_iter * 8 - 1) / (rows_per_iter * 8),
+                                                   std::max(1, kNumSMs * 4 / A)));
+  chunks = std::max(chunks, 1);
+  dim3 grid(chunks, A);
+  const size_t smem = static_cast<size_t>(table_gs) * sizeof(float);
+  if (dtype == kBF16)
+    act_table_grad_kernel<__nv_bfloat16><<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(gzin), ld, col0, act, act_ld, n_act, C, B, d_table, table_gs);
+  else
+    act_table_grad_kernel<float><<<grid, kThreads, smem, s>>>(static_cast<const float*>(gzin), ld, col0, act, act_ld, n_act, C, B, d_table, table_gs);
+  MFVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused Adam: one pass, 28 B / parameter (+2 B when the bf16 shadow is refreshed in the same pass).
+// Same operation order as torch.optim.Adam (single-tensor path): lerp, addcmul, sqrt / bc2_sqrt + eps, addcdiv.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v,
+                                                        __nv_bfloat16* __restrict__ shadow, int64_t n4,
+                                                        float one_minus_b1, float b2, float one_minus_b2,
+                                                        float step_size, float bc2_sqrt, float eps) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = ldg_stream4(g + i * 4);
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+#define MFVAE_ADAM_1(c)                                           \
+    mm.c = mm.c + one_minus_b1 * (gg.c - mm.c);                   \
+    vv.c = vv.c * b2 + one_minus_b2 * gg.c * gg.c;                \
+    pp.c = pp.c - step_size * (mm.c / (sqrtf(vv.c) / bc2_sqrt + eps));
+    MFVAE_ADAM_1(x) MFVAE_ADAM_1(y) MFVAE_ADAM_1(z) MFVAE_ADAM_1(w)
+#undef MFVAE_ADAM_1
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (shadow) store4<__nv_bfloat16>(shadow + i * 4, pp);
+  }
+}
+
+int launch_adam(float* p, const float* g, float* m, float* v, __nv_bfloat16* shadow, int64_t n,
+                float lr, float b1, float b2, float eps, int64_t t, cudaStream_t s) {
+  MFVAE_CHECK(n % 4 == 0, "adam: element count must be a multiple of 4");
+  MFVAE_CHECK(t >= 1, "adam: step count starts at 1");
+  const double bc1 = 1.0 - pow(static_cast<double>(b1), static_cast<double>(t));
+  const double bc2 = 1.0 - pow(static_cast<double>(b2), static_cast<double>(t));
+  const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+  const float bc2_sqrt = static_cast<float>(sqrt(bc2));
+  adam_kernel<<<grid_for(n / 4), kThreads, 0, s>>>(p, g, m, v, shadow, n / 4, 1.f - b1, b2, 1.f - b2,
+                                                  step_size, bc2_sqrt, eps);
+  MFVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(kThreads) cast_bf16_kernel(const float* __restrict__ src,
+                                                             __nv_bfloat16* __restrict__ dst, int64_t n4) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    store4<__nv_bfloat16>(dst + i * 4, ldg_stream4(src + i * 4));
+}
+
+int launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t s) {
+  MFVAE_CHECK(n % 4 == 0, "cast: element count must be a multiple of 4");
+  cast_bf16_kernel<<<grid_for(n / 4), kThreads, 0, s>>>(src, dst, n / 4);
+  MFVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) cast2d_kernel(const float* __restrict__ src, int64_t src_ld, T* __restrict__ dst,
+                                                          int64_t dst_ld, int64_t B, int width) {
+  const int64_t total = B * width;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = i / width;
+    const int c = static_cast<int>(i - b * width);
+    dst[b * dst_ld + c] = from_f<T>(src ? src[b * src_ld + c] : 0.f);
+  }
+}
+
+int launch_cast2d(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int dtype, int64_t B, int width, cudaStream_t s) {
+  const int grid = grid_for(B * width);
+  if (dtype == kBF16) cast2d_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(src, src_ld, static_cast<__nv_bfloat16*>(dst), dst_ld, B, width);
+  else                cast2d_kernel<float><<<grid, kThreads, 0, s>>>(src, src_ld, static_cast<float*>(dst), dst_ld, B, width);
+  MFVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(kThreads) philox_normal_kernel(float* out, int64_t B, int wq, uint64_t seed,
+                                                                 uint64_t step, int64_t sample0) {
+  const int64_t total = B * wq;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = i / wq;
+    const int q = static_cast<int>(i - b * wq);
+    reinterpret_cast<float4*>(out)[i] = philox_normal4(seed, step, static_cast<uint64_t>(sample0 + b), q);
+  }
+}
+
+int launch_philox_normal(float* out, int64_t B, int width, uint64_t seed, uint64_t step, int64_t sample0,
+                         cudaStream_t s) {
+  MFVAE_CHECK(width % 4 == 0, "philox_normal: width must be a multiple of 4");
+  philox_normal_kernel<<<grid_for(B * (width / 4)), kThreads, 0, s>>>(out, B, width / 4, seed, step, sample0);
+  MFVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void loss_total_kernel(float* losses, float r_weight, float kl_weight) {
+  losses[0] = losses[1] + r_weight * losses[2] + kl_weight * losses[3];
+}
+
+int launch_loss_total(float* losses, float r_weight, float kl_weight, cudaStream_t s) {
+  loss_total_kernel<<<1, 1, 0, s>>>(losses, r_weight, kl_weight);
+  MFVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mfvae

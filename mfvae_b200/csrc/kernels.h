@@ -1,0 +1,107 @@
+// kernels.h — internal launch API shared by plan.cu / api.cu (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+namespace mfvae {
+
+enum DType { kF32 = 0, kBF16 = 1 };
+static inline size_t dtype_size(int dt) { return dt == kBF16 ? 2 : 4; }
+
+// ---- bandwidth-bound kernels (elementwise.cu) -------------------------------------------------
+struct StageArgs {
+  const float* obs; int obs_ld;          // [B, S]
+  const float* act; int act_ld;          // [B, A] fp32-coded
+  const float* idx;                      // [B, A] fp32-coded or nullptr
+  const float* idx_emb;                  // [A, I] fp32 master
+  const float* act_table; int64_t act_table_gs; int n_act_max;  // [A][n_act_max][C] fp32 master
+  const int32_t* obs_off; const int32_t* obs_dim; const int32_t* n_act;   // device [A]
+  void* x0; int x0_ld; int64_t x0_gs;    // [A][B][K0p]
+  void* zin; int zin_ld;                 // [B, Din]: act-emb written at column A*L + a*C
+  int A, I, L, C, B;
+  int dtype;
+};
+int launch_stage(const StageArgs& a, cudaStream_t s);
+
+struct ReparamArgs {
+  const float* mu; const float* lv;      // element (b,a,j) at p + a*lat_as + b*lat_bs + j
+  int64_t lat_as, lat_bs;
+  const float* eps; int64_t eps_ld;      // [B, A*L] or nullptr -> Philox
+  void* z; int64_t z_ld; int z_dtype;    // z[b][a*L + j]
+  int64_t B; int A, L;
+  uint64_t seed, step; int64_t sample0;
+  float kl_scale;                        // 1 / batch_global
+  float* kl_out;                         // [1]
+  float* scratch;                        // >= 4096 floats (partials + ticket)
+};
+int launch_reparam_kl_fwd(const ReparamArgs& a, cudaStream_t s);
+
+struct ReparamBwdArgs {
+  const void* gz; int64_t gz_ld; int g_dtype;   // dL/dz [B, >= A*L]
+  const float* mu; const float* lv; int64_t lat_as, lat_bs;
+  const float* eps; int64_t eps_ld;
+  void* dlat; int64_t dlat_as, dlat_bs; int d_dtype;   // [A][B][2L]
+  int64_t B; int A, L;
+  uint64_t seed, step; int64_t sample0;
+  float kl_scale;                        // kl_weight / batch_global
+  const float* glat;                     // optional upstream d/d(mu, logvar), same layout as mu/lv base (fp32)
+};
+int launch_reparam_kl_bwd(const ReparamBwdArgs& a, cudaStream_t s);
+
+struct ReconLossArgs {
+  const float* recon; int64_t recon_ld;
+  const float* target; int64_t target_ld;
+  void* grad; int64_t grad_ld; int grad_dtype;   // may be nullptr (forward value only)
+  int64_t B; int width;
+  int huber;
+  float grad_scale;      // weight / count_global
+  float loss_scale;      // 1 / count_global
+  float* loss_out;       // [1]
+  float* scratch;        // >= 4096 floats
+};
+int launch_recon_loss(const ReconLossArgs& a, cudaStream_t s);
+
+// out[g][n] += sum_b X[g][b][n]   (fp32 atomics; `out` must be zeroed by the caller)
+int launch_colsum(const void* x, int dtype, int G, int64_t B, int N, int64_t ld, int64_t gs,
+                  float* out, int64_t out_gs, cudaStream_t s);
+
+// d_emb[idx[b][a]][i] += gx0[a][b][i]  (general index path)
+int launch_idx_emb_scatter(const void* gx0, int dtype, int64_t gs, int64_t ld, const float* idx, int idx_ld,
+                           int A, int I, int64_t B, float* d_emb, cudaStream_t s);
+// d_table[a][act[b][a]][c] += gzin[b][col0 + a*C + c]
+int launch_act_table_grad(const void* gzin, int dtype, int64_t ld, int col0, const float* act, int act_ld,
+                          const int32_t* n_act, int A, int C, int64_t B, float* d_table, int64_t table_gs,
+                          cudaStream_t s);
+
+int launch_adam(float* p, const float* g, float* m, float* v, __nv_bfloat16* shadow, int64_t n,
+                float lr, float b1, float b2, float eps, int64_t t, cudaStream_t s);
+// dst[b][c] = src[b][c] for c < width (fp32 -> activation dtype); src == nullptr writes zeros
+int launch_cast2d(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int dtype, int64_t B, int width, cudaStream_t s);
+int launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t s);
+int launch_philox_normal(float* out, int64_t B, int width, uint64_t seed, uint64_t step, int64_t sample0,
+                         cudaStream_t s);
+// losses[0] = s + r_w * r + kl_w * kl  given losses[1..3]
+int launch_loss_total(float* losses, float r_weight, float kl_weight, cudaStream_t s);
+
+// ---- GEMM (gemm_simt.cu / gemm_tc.cu) --------------------------------------------------------
+enum Epilogue { kEpiNone = 0, kEpiBias = 1, kEpiBiasRelu = 2, kEpiReluMask = 3, kEpiAccum = 4 };
+
+struct GemmOp {
+  int G = 1, M = 0, N = 0, K = 0;
+  int dtype = kF32;                           // operand type
+  const void* A = nullptr; int64_t a_gs = 0, a_rs = 0, a_cs = 0;   // A(m,k)
+  const void* B = nullptr; int64_t b_gs = 0, b_rs = 0, b_cs = 0;   // B(n,k)
+  void* C = nullptr; int64_t c_gs = 0, c_ld = 0; int c_dtype = kF32;
+  const float* bias = nullptr; int64_t bias_gs = 0;
+  int epi = kEpiNone;
+  const void* aux = nullptr; int64_t aux_gs = 0, aux_ld = 0;      // relu-mask source, operand dtype
+  int split_k = 1;                            // > 1 requires kEpiAccum into a zeroed fp32 C
+};
+int gemm_simt(const GemmOp& op, cudaStream_t s);
+
+// tcgen05 path: tensor maps are built once per op (plan time) and reused every step.
+struct TcPlan;
+int gemm_tc_plan(const GemmOp& op, TcPlan** out);       // validates alignment, encodes CUtensorMaps
+int gemm_tc_run(const TcPlan* p, cudaStream_t s);
+void gemm_tc_free(TcPlan* p);
+
+}  // namespace mfvae

@@ -1,0 +1,696 @@
+// plan.cu — handle, arena / workspace layout and the op sequence of one MAVAE train step.
+//
+// Reference data flow being reproduced (all citations /root/reference/torch_ver):
+//   forward   model.py:134-173      loss  model.py:19-40      backward  main.py:92-93      Adam  main.py:97
+//
+// HBM layout:
+//   parameter arena (fp32 master | grad | m | v | bf16 shadow share one element layout)
+//     [ idx_emb | dec hidden l: Ws_l, Wr_l, bs_l, br_l | Ws_out, bs_out, Wr_out, br_out, rlW, rlb ] <- Adam prefix
+//     [ enc l: W[A][N_l][K_l], b[A][N_l] | action tables [A][n_act_max][C] ]
+//   activation workspace for a bound batch B
+//     X0[A][B][K0p]  XE_l[A][B][H_l]  LAT[A][B][2L](fp32)  ZIN[B][A(L+C)]  HD_l[B][2 H_l] (state | reward halves)
+//     RS[B][Sp](fp32) RR0[B][Ap] RR[B][Ap](fp32)  and the matching gradient buffers.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "kernels.h"
+
+namespace mfvae {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(const char* file, int line, const std::string& msg) {
+  const char* base = strrchr(file, '/');
+  g_last_error = std::string(base ? base + 1 : file) + ":" + std::to_string(line) + ": " + msg;
+  return 1;
+}
+
+struct Span { int64_t off = 0; int rows = 0, cols = 0, ld = 0; };
+
+}  // namespace mfvae
+
+using namespace mfvae;
+
+struct MfvaeHandle_ {
+  MfvaeConfig cfg{};
+  int device = 0;
+  std::vector<int32_t> obs_dim, n_act, obs_off;
+  int A = 0, I = 0, L = 0, C = 0, S = 0, Sp = 0, Ap = 0, Ip = 0, Din = 0, K0p = 0, nact_max = 0;
+  int ne = 0, nd = 0;                       // number of Linear layers in encoder / decoder
+  std::vector<int> encN, encK;              // per encoder layer (K padded)
+  std::vector<int> decH;                    // decoder hidden widths
+  int dtype = kF32;
+  bool use_tc = false;
+
+  // arena layout
+  Span idx_emb, rlW, rlb, sOutW, sOutB, rOutW, rOutB, actT;
+  std::vector<Span> decW, decB;             // per hidden layer: rows = 2*H (state rows then reward rows)
+  std::vector<Span> encW, encB;             // rows = A*N_l
+  int64_t arena_elems = 0, optimized_elems = 0, reg3_begin = 0, reg2_begin = 0, enc_begin = 0;
+  std::vector<MfvaeTensorInfo> table;
+  MfvaeArenas ar{};
+
+  // device constants
+  int32_t* d_meta = nullptr;                // obs_off | obs_dim | n_act
+
+  // workspace
+  char* ws = nullptr; int64_t ws_bytes = 0; int B = 0;
+  struct Buf { int64_t off = 0; int64_t ld = 0; int64_t gs = 0; };
+  Buf X0, LAT, ZIN, RS, RR0, RR, DRS, DRR, DRR0, GZIN, DLAT, GX0;
+  std::vector<Buf> XE, DXE, HD, DHD;
+  int64_t off_losses = 0, off_scratch = 0;
+
+  // GEMM ops
+  std::vector<GemmOp> gemms;
+  std::vector<TcPlan*> tc;
+  std::vector<int> g_enc_fwd, g_enc_wg, g_enc_dg, g_dec_fwd, g_dec_wg, g_dec_dg;
+  int g_sout_fwd = -1, g_rout_fwd = -1, g_rl_fwd = -1;
+  int g_sout_wg = -1, g_sout_dg = -1, g_rout_wg = -1, g_rout_dg = -1, g_rl_wg = -1, g_rl_dg = -1;
+
+  // gradient buckets (arena ranges) and their completion events
+  struct Bucket { int64_t begin, end; cudaEvent_t ev; };
+  std::vector<Bucket> buckets;
+};
+
+namespace mfvae {
+
+static int64_t take(int64_t& cursor, int64_t n) { int64_t o = cursor; cursor += round_up(n, 8); return o; }
+
+static void add_info(MfvaeHandle_* h, int kind, int agent, int layer, int rows, int cols, int ld, int64_t off) {
+  MfvaeTensorInfo t{kind, agent, layer, rows, cols, ld, off};
+  h->table.push_back(t);
+}
+
+static int build_layout(MfvaeHandle_* h) {
+  const MfvaeConfig& c = h->cfg;
+  h->A = c.n_agents; h->I = c.idx_features; h->L = c.latent; h->C = c.act_features;
+  MFVAE_CHECK(h->A >= 1 && h->A <= 4096, "n_agents out of range");
+  MFVAE_CHECK(h->I % 8 == 0 && h->L % 8 == 0 && h->C % 8 == 0, "idx_features, latent and act_features must be multiples of 8");
+  MFVAE_CHECK(c.n_enc_hidden >= 1 && c.n_enc_hidden <= MFVAE_MAX_HIDDEN, "n_enc_hidden out of range");
+  MFVAE_CHECK(c.n_dec_hidden >= 1 && c.n_dec_hidden <= MFVAE_MAX_HIDDEN, "n_dec_hidden out of range");
+  int maxo = 0; h->S = 0; h->nact_max = 0;
+  h->obs_off.resize(h->A);
+  for (int a = 0; a < h->A; ++a) {
+    MFVAE_CHECK(h->obs_dim[a] >= 1 && h->n_act[a] >= 1, "obs_dim / n_act must be positive");
+    h->obs_off[a] = h->S; h->S += h->obs_dim[a];
+    maxo = std::max(maxo, h->obs_dim[a]); h->nact_max = std::max(h->nact_max, h->n_act[a]);
+  }
+  h->Sp = static_cast<int>(round_up(h->S, 8)); h->Ap = static_cast<int>(round_up(h->A, 8));
+  h->Ip = h->I;
+  h->K0p = static_cast<int>(round_up(h->I + maxo, 8));
+  h->Din = h->A * (h->L + h->C);
+  h->ne = c.n_enc_hidden + 1; h->nd = c.n_dec_hidden + 1;
+  h->encN.clear(); h->encK.clear(); h->decH.clear();
+  for (int l = 0; l < h->ne; ++l) {
+    const int n = (l < c.n_enc_hidden) ? c.enc_hidden[l] : 2 * h->L;
+    const int k = (l == 0) ? h->K0p : c.enc_hidden[l - 1];
+    MFVAE_CHECK(n % 8 == 0, "encoder hidden widths must be multiples of 8");
+    h->encN.push_back(n); h->encK.push_back(k);
+  }
+  for (int l = 0; l < c.n_dec_hidden; ++l) {
+    MFVAE_CHECK(c.dec_hidden[l] % 8 == 0, "decoder hidden widths must be multiples of 8");
+    h->decH.push_back(c.dec_hidden[l]);
+  }
+  h->dtype = (c.precision == MFVAE_PREC_BF16) ? kBF16 : kF32;
+  int engine = c.engine;
+  if (engine == MFVAE_ENGINE_AUTO) engine = (h->dtype == kBF16) ? MFVAE_ENGINE_TCGEN05 : MFVAE_ENGINE_SIMT;
+  MFVAE_CHECK(!(engine == MFVAE_ENGINE_TCGEN05 && h->dtype != kBF16), "the tcgen05 engine computes in bf16");
+  h->use_tc = (engine == MFVAE_ENGINE_TCGEN05);
+
+  // ---- arena ----
+  int64_t cur = 0;
+  h->table.clear();
+  h->idx_emb = {take(cur, static_cast<int64_t>(h->A) * h->I), h->A, h->I, h->I};
+  add_info(h, MFVAE_T_IDX_EMB, -1, -1, h->A, h->I, h->I, h->idx_emb.off);
+  h->reg2_begin = cur;
+  h->decW.resize(c.n_dec_hidden); h->decB.resize(c.n_dec_hidden);
+  for (int l = 0; l < c.n_dec_hidden; ++l) {
+    const int H = h->decH[l], K = (l == 0) ? h->Din : h->decH[l - 1];
+    h->decW[l] = {take(cur, 2LL * H * K), 2 * H, K, K};
+    h->decB[l] = {take(cur, 2LL * H), 1, 2 * H, 2 * H};
+    add_info(h, MFVAE_T_SDEC_W, -1, l, H, K, K, h->decW[l].off);
+    add_info(h, MFVAE_T_RDEC_W, -1, l, H, K, K, h->decW[l].off + static_cast<int64_t>(H) * K);
+    add_info(h, MFVAE_T_SDEC_B, -1, l, 1, H, H, h->decB[l].off);
+    add_info(h, MFVAE_T_RDEC_B, -1, l, 1, H, H, h->decB[l].off + H);
+  }
+  h->reg3_begin = cur;
+  const int HL = h->decH.back();
+  h->sOutW = {take(cur, static_cast<int64_t>(h->S) * HL), h->S, HL, HL};
+  h->sOutB = {take(cur, h->S), 1, h->S, h->S};
+  h->rOutW = {take(cur, static_cast<int64_t>(h->A) * HL), h->A, HL, HL};
+  h->rOutB = {take(cur, h->A), 1, h->A, h->A};
+  h->rlW = {take(cur, static_cast<int64_t>(h->A) * h->Ap), h->A, h->A, h->Ap};
+  h->rlb = {take(cur, h->A), 1, h->A, h->A};
+  add_info(h, MFVAE_T_SDEC_W, -1, c.n_dec_hidden, h->S, HL, HL, h->sOutW.off);
+  add_info(h, MFVAE_T_SDEC_B, -1, c.n_dec_hidden, 1, h->S, h->S, h->sOutB.off);
+  add_info(h, MFVAE_T_RDEC_W, -1, c.n_dec_hidden, h->A, HL, HL, h->rOutW.off);
+  add_info(h, MFVAE_T_RDEC_B, -1, c.n_dec_hidden, 1, h->A, h->A, h->rOutB.off);
+  add_info(h, MFVAE_T_RLIN_W, -1, -1, h->A, h->A, h->Ap, h->rlW.off);
+  add_info(h, MFVAE_T_RLIN_B, -1, -1, 1, h->A, h->A, h->rlb.off);
+  h->enc_begin = cur;
+  h->encW.resize(h->ne); h->encB.resize(h->ne);
+  for (int l = 0; l < h->ne; ++l) {
+    const int N = h->encN[l], K = h->encK[l];
+    h->encW[l] = {take(cur, static_cast<int64_t>(h->A) * N * K), h->A * N, K, K};
+    h->encB[l] = {take(cur, static_cast<int64_t>(h->A) * N), h->A, N, N};
+    for (int a = 0; a < h->A; ++a) {
+      const int kc = (l == 0) ? h->I + h->obs_dim[a] : K;
+      add_info(h, MFVAE_T_ENC_W, a, l, N, kc, K, h->encW[l].off + static_cast<int64_t>(a) * N * K);
+      add_info(h, MFVAE_T_ENC_B, a, l, 1, N, N, h->encB[l].off + static_cast<int64_t>(a) * N);
+    }
+  }
+  h->actT = {take(cur, static_cast<int64_t>(h->A) * h->nact_max * h->C), h->A * h->nact_max, h->C, h->C};
+  for (int a = 0; a < h->A; ++a)
+    add_info(h, MFVAE_T_ACT_TABLE, a, -1, h->n_act[a], h->C, h->C, h->actT.off + static_cast<int64_t>(a) * h->nact_max * h->C);
+  h->arena_elems = cur;
+  h->optimized_elems = c.optimize_encoders ? cur : h->enc_begin;
+  return 0;
+}
+
+// ---- workspace ---------------------------------------------------------------------------------
+static int64_t layout_workspace(MfvaeHandle_* h, int B) {
+  const int64_t es = dtype_size(h->dtype);
+  int64_t cur = 0;
+  auto alloc = [&](int64_t bytes) { int64_t o = cur; cur += round_up(bytes, 256); return o; };
+  auto mk = [&](int64_t groups, int64_t ld, int64_t esz, bool grouped_rows) {
+    MfvaeHandle_::Buf b;
+    b.ld = ld; b.gs = grouped_rows ? static_cast<int64_t>(B) * ld : 0;
+    b.off = alloc(groups * B * ld * esz);
+    return b;
+  };
+  const int A = h->A;
+  h->X0 = mk(A, h->K0p, es, true);
+  h->XE.clear(); h->DXE.clear(); h->HD.clear(); h->DHD.clear();
+  for (int l = 0; l + 1 < h->ne; ++l) h->XE.push_back(mk(A, h->encN[l], es, true));
+  h->LAT = mk(A, 2 * h->L, 4, true);
+  h->ZIN = mk(1, h->Din, es, false);
+  for (int l = 0; l < h->cfg.n_dec_hidden; ++l) h->HD.push_back(mk(1, 2 * h->decH[l], es, false));
+  h->RS = mk(1, h->Sp, 4, false);
+  h->RR0 = mk(1, h->Ap, es, false);
+  h->RR = mk(1, h->Ap, 4, false);
+  h->DRS = mk(1, h->Sp, es, false);
+  h->DRR = mk(1, h->Ap, es, false);
+  h->DRR0 = mk(1, h->Ap, es, false);
+  for (int l = 0; l < h->cfg.n_dec_hidden; ++l) h->DHD.push_back(mk(1, 2 * h->decH[l], es, false));
+  h->GZIN = mk(1, h->Din, es, false);
+  h->DLAT = mk(A, 2 * h->L, es, true);
+  for (int l = 0; l + 1 < h->ne; ++l) h->DXE.push_back(mk(A, h->encN[l], es, true));
+  h->GX0 = mk(A, h->Ip, es, true);
+  h->off_losses = alloc(64 * sizeof(float));
+  h->off_scratch = alloc(3 * 4096 * sizeof(float));
+  return cur;
+}
+
+static void free_plans(MfvaeHandle_* h) {
+  for (TcPlan* p : h->tc) if (p) gemm_tc_free(p);
+  h->tc.clear(); h->gemms.clear();
+  h->g_enc_fwd.clear(); h->g_enc_wg.clear(); h->g_enc_dg.clear();
+  h->g_dec_fwd.clear(); h->g_dec_wg.clear(); h->g_dec_dg.clear();
+}
+
+static int pick_split_k(int G, int M, int N, int K) {
+  const int64_t tiles = static_cast<int64_t>(G) * ((M + 127) / 128) * ((N + 127) / 128);
+  int64_t want = (2LL * kNumSMs + tiles - 1) / tiles;
+  int64_t maxs = std::max(1, K / 256);
+  return static_cast<int>(std::max<int64_t>(1, std::min(want, maxs)));
+}
+
+static int build_ops(MfvaeHandle_* h) {
+  free_plans(h);
+  const int B = h->B, A = h->A, dt = h->dtype;
+  const int64_t es = dtype_size(dt);
+  char* ws = h->ws;
+  const char* W = (dt == kBF16) ? static_cast<const char*>(h->ar.d_shadow_bf16) : reinterpret_cast<const char*>(h->ar.d_param);
+  MFVAE_CHECK(W != nullptr, "arenas are not bound (bf16 precision needs d_shadow_bf16)");
+  float* P = h->ar.d_param; float* Gd = h->ar.d_grad;
+  MFVAE_CHECK(P && Gd, "arenas are not bound");
+  auto wptr = [&](int64_t off) { return static_cast<const void*>(W + off * es); };
+  auto buf = [&](const MfvaeHandle_::Buf& b) { return static_cast<void*>(ws + b.off); };
+  auto push = [&](const GemmOp& op) { h->gemms.push_back(op); return static_cast<int>(h->gemms.size()) - 1; };
+  auto fwd = [&](int G, int M, int N, int K, const void* Ain, int64_t a_gs, int64_t a_ld, const void* Wt, int64_t w_gs, int64_t w_ld,
+                 void* Cout, int64_t c_gs, int64_t c_ld, int c_dtype, const float* bias, int64_t bias_gs, bool relu) {
+    GemmOp o; o.G = G; o.M = M; o.N = N; o.K = K; o.dtype = dt;
+    o.A = Ain; o.a_gs = a_gs; o.a_rs = a_ld; o.a_cs = 1;
+    o.B = Wt; o.b_gs = w_gs; o.b_rs = w_ld; o.b_cs = 1;
+    o.C = Cout; o.c_gs = c_gs; o.c_ld = c_ld; o.c_dtype = c_dtype;
+    o.bias = bias; o.bias_gs = bias_gs; o.epi = relu ? kEpiBiasRelu : kEpiBias;
+    return push(o);
+  };
+  // dW[g] (N_out x K_in) += D[g]^T (N_out x B) * X[g] (B x K_in)
+  auto wgrad = [&](int G, int Nout, int Kin, const void* D, int64_t d_gs, int64_t d_ld, const void* X, int64_t x_gs, int64_t x_ld,
+                   int64_t gw_off, int64_t gw_gs, int64_t gw_ld) {
+    GemmOp o; o.G = G; o.M = Nout; o.N = Kin; o.K = B; o.dtype = dt;
+    o.A = D; o.a_gs = d_gs; o.a_rs = 1; o.a_cs = d_ld;
+    o.B = X; o.b_gs = x_gs; o.b_rs = 1; o.b_cs = x_ld;
+    o.C = Gd + gw_off; o.c_gs = gw_gs; o.c_ld = gw_ld; o.c_dtype = kF32;
+    o.epi = kEpiAccum; o.split_k = pick_split_k(G, Nout, Kin, B);
+    return push(o);
+  };
+  // dX[g] (B x K_in) = D[g] (B x N_out) * W[g] (N_out x K_in)  [* (mask > 0)]
+  auto dgrad = [&](int G, int Kin, int Nout, const void* D, int64_t d_gs, int64_t d_ld, const void* Wt, int64_t w_gs, int64_t w_ld,
+                   void* dX, int64_t dx_gs, int64_t dx_ld, const void* mask, int64_t m_gs, int64_t m_ld) {
+    GemmOp o; o.G = G; o.M = B; o.N = Kin; o.K = Nout; o.dtype = dt;
+    o.A = D; o.a_gs = d_gs; o.a_rs = d_ld; o.a_cs = 1;
+    o.B = Wt; o.b_gs = w_gs; o.b_rs = 1; o.b_cs = w_ld;
+    o.C = dX; o.c_gs = dx_gs; o.c_ld = dx_ld; o.c_dtype = dt;
+    o.epi = mask ? kEpiReluMask : kEpiNone; o.aux = mask; o.aux_gs = m_gs; o.aux_ld = m_ld;
+    return push(o);
+  };
+
+  // ---- encoders (G = A) ----
+  for (int l = 0; l < h->ne; ++l) {
+    const int N = h->encN[l], K = h->encK[l];
+    const MfvaeHandle_::Buf& in = (l == 0) ? h->X0 : h->XE[l - 1];
+    const bool last = (l + 1 == h->ne);
+    const MfvaeHandle_::Buf& out = last ? h->LAT : h->XE[l];
+    h->g_enc_fwd.push_back(fwd(A, B, N, K, buf(in), in.gs, in.ld, wptr(h->encW[l].off), static_cast<int64_t>(N) * K, K,
+                               buf(out), out.gs, out.ld, last ? kF32 : dt, P + h->encB[l].off, N, !last));
+  }
+  for (int l = 0; l < h->ne; ++l) {
+    const int N = h->encN[l], K = h->encK[l];
+    const MfvaeHandle_::Buf& in = (l == 0) ? h->X0 : h->XE[l - 1];
+    const MfvaeHandle_::Buf& D = (l + 1 == h->ne) ? h->DLAT : h->DXE[l];
+    h->g_enc_wg.push_back(wgrad(A, N, K, buf(D), D.gs, D.ld, buf(in), in.gs, in.ld, h->encW[l].off, static_cast<int64_t>(N) * K, K));
+    if (l == 0) {   // only the id-embedding columns of dX0 are needed
+      h->g_enc_dg.push_back(dgrad(A, h->I, N, buf(D), D.gs, D.ld, wptr(h->encW[0].off), static_cast<int64_t>(N) * K, K,
+                                  buf(h->GX0), h->GX0.gs, h->GX0.ld, nullptr, 0, 0));
+    } else {
+      const MfvaeHandle_::Buf& dx = h->DXE[l - 1];
+      h->g_enc_dg.push_back(dgrad(A, K, N, buf(D), D.gs, D.ld, wptr(h->encW[l].off), static_cast<int64_t>(N) * K, K,
+                                  buf(dx), dx.gs, dx.ld, buf(in), in.gs, in.ld));
+    }
+  }
+  // ---- decoders: hidden layers (layer 0 fused over both decoders, others G = 2 over column halves) ----
+  const int nh = h->cfg.n_dec_hidden;
+  for (int l = 0; l < nh; ++l) {
+    const int H = h->decH[l];
+    if (l == 0) {
+      h->g_dec_fwd.push_back(fwd(1, B, 2 * H, h->Din, buf(h->ZIN), 0, h->ZIN.ld, wptr(h->decW[0].off), 0, h->Din,
+                                 buf(h->HD[0]), 0, h->HD[0].ld, dt, P + h->decB[0].off, 0, true));
+      h->g_dec_wg.push_back(wgrad(1, 2 * H, h->Din, buf(h->DHD[0]), 0, h->DHD[0].ld, buf(h->ZIN), 0, h->ZIN.ld,
+                                  h->decW[0].off, 0, h->Din));
+      h->g_dec_dg.push_back(dgrad(1, h->Din, 2 * H, buf(h->DHD[0]), 0, h->DHD[0].ld, wptr(h->decW[0].off), 0, h->Din,
+                                  buf(h->GZIN), 0, h->GZIN.ld, nullptr, 0, 0));
+    } else {
+      const int K = h->decH[l - 1];
+      char* in = ws + h->HD[l - 1].off; char* out = ws + h->HD[l].off;
+      char* D = ws + h->DHD[l].off; char* dx = ws + h->DHD[l - 1].off;
+      h->g_dec_fwd.push_back(fwd(2, B, H, K, in, K, h->HD[l - 1].ld, wptr(h->decW[l].off), static_cast<int64_t>(H) * K, K,
+                                 out, H, h->HD[l].ld, dt, P + h->decB[l].off, H, true));
+      h->g_dec_wg.push_back(wgrad(2, H, K, D, H, h->DHD[l].ld, in, K, h->HD[l - 1].ld, h->decW[l].off, static_cast<int64_t>(H) * K, K));
+      h->g_dec_dg.push_back(dgrad(2, K, H, D, H, h->DHD[l].ld, wptr(h->decW[l].off), static_cast<int64_t>(H) * K, K,
+                                  dx, K, h->DHD[l - 1].ld, in, K, h->HD[l - 1].ld));
+    }
+  }
+  // ---- output layers ----
+  {
+    const int HL = h->decH.back();
+    char* hs = ws + h->HD[nh - 1].off;                    // state half
+    char* hr = hs + static_cast<int64_t>(HL) * es;        // reward half
+    char* dhs = ws + h->DHD[nh - 1].off; char* dhr = dhs + static_cast<int64_t>(HL) * es;
+    const int64_t hld = h->HD[nh - 1].ld;
+    h->g_sout_fwd = fwd(1, B, h->S, HL, hs, 0, hld, wptr(h->sOutW.off), 0, HL, buf(h->RS), 0, h->RS.ld, kF32, P + h->sOutB.off, 0, false);
+    h->g_rout_fwd = fwd(1, B, A, HL, hr, 0, hld, wptr(h->rOutW.off), 0, HL, buf(h->RR0), 0, h->RR0.ld, dt, P + h->rOutB.off, 0, false);
+    h->g_rl_fwd = fwd(1, B, A, A, buf(h->RR0), 0, h->RR0.ld, wptr(h->rlW.off), 0, h->Ap, buf(h->RR), 0, h->RR.ld, kF32, P + h->rlb.off, 0, false);
+    h->g_rl_wg = wgrad(1, A, A, buf(h->DRR), 0, h->DRR.ld, buf(h->RR0), 0, h->RR0.ld, h->rlW.off, 0, h->Ap);
+    h->g_rl_dg = dgrad(1, A, A, buf(h->DRR), 0, h->DRR.ld, wptr(h->rlW.off), 0, h->Ap, buf(h->DRR0), 0, h->DRR0.ld, nullptr, 0, 0);
+    h->g_rout_wg = wgrad(1, A, HL, buf(h->DRR0), 0, h->DRR0.ld, hr, 0, hld, h->rOutW.off, 0, HL);
+    h->g_rout_dg = dgrad(1, HL, A, buf(h->DRR0), 0, h->DRR0.ld, wptr(h->rOutW.off), 0, HL, dhr, 0, hld, hr, 0, hld);
+    h->g_sout_wg = wgrad(1, h->S, HL, buf(h->DRS), 0, h->DRS.ld, hs, 0, hld, h->sOutW.off, 0, HL);
+    h->g_sout_dg = dgrad(1, HL, h->S, buf(h->DRS), 0, h->DRS.ld, wptr(h->sOutW.off), 0, HL, dhs, 0, hld, hs, 0, hld);
+  }
+  h->tc.assign(h->gemms.size(), nullptr);
+  if (h->use_tc) {
+    for (size_t i = 0; i < h->gemms.size(); ++i) MFVAE_TRY(gemm_tc_plan(h->gemms[i], &h->tc[i]));
+  }
+  return 0;
+}
+
+static int run_gemm(MfvaeHandle_* h, int i, cudaStream_t s) {
+  if (h->use_tc) return gemm_tc_run(h->tc[i], s);
+  return gemm_simt(h->gemms[i], s);
+}
+
+static int check_ready(MfvaeHandle_* h, const MfvaeBatch* b) {
+  MFVAE_CHECK(h != nullptr && b != nullptr, "null handle or batch");
+  MFVAE_CHECK(h->device >= 0, "layout-only handle: there is no CPU path, create the handle on a CUDA device");
+  MFVAE_CHECK(h->ws != nullptr, "workspace is not bound");
+  MFVAE_CHECK(b->batch == h->B, "batch size differs from the bound workspace");
+  MFVAE_CHECK(b->d_obs && b->d_act, "batch needs d_obs and d_act");
+  MFVAE_CHECK(b->batch_global >= b->batch, "batch_global must be >= batch");
+  return 0;
+}
+
+static float* losses_ptr(MfvaeHandle_* h) { return reinterpret_cast<float*>(h->ws + h->off_losses); }
+static float* scratch_ptr(MfvaeHandle_* h, int i) { return reinterpret_cast<float*>(h->ws + h->off_scratch) + 4096 * i; }
+
+static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, cudaStream_t s) {
+  MFVAE_TRY(check_ready(h, b));
+  StageArgs st{};
+  st.obs = b->d_obs; st.obs_ld = h->S; st.act = b->d_act; st.act_ld = h->A; st.idx = b->d_idx;
+  st.idx_emb = h->ar.d_param + h->idx_emb.off;
+  st.act_table = h->ar.d_param + h->actT.off; st.act_table_gs = static_cast<int64_t>(h->nact_max) * h->C; st.n_act_max = h->nact_max;
+  st.obs_off = h->d_meta; st.obs_dim = h->d_meta + h->A; st.n_act = h->d_meta + 2 * h->A;
+  st.x0 = h->ws + h->X0.off; st.x0_ld = static_cast<int>(h->X0.ld); st.x0_gs = h->X0.gs;
+  st.zin = h->ws + h->ZIN.off; st.zin_ld = static_cast<int>(h->ZIN.ld);
+  st.A = h->A; st.I = h->I; st.L = h->L; st.C = h->C; st.B = h->B; st.dtype = h->dtype;
+  MFVAE_TRY(launch_stage(st, s));
+  for (int l = 0; l < h->ne; ++l) MFVAE_TRY(run_gemm(h, h->g_enc_fwd[l], s));
+  ReparamArgs rp{};
+  const float* lat = reinterpret_cast<const float*>(h->ws + h->LAT.off);
+  rp.mu = lat; rp.lv = lat + h->L; rp.lat_as = h->LAT.gs; rp.lat_bs = h->LAT.ld;
+  rp.eps = b->d_eps; rp.eps_ld = static_cast<int64_t>(h->A) * h->L;
+  rp.z = h->ws + h->ZIN.off; rp.z_ld = h->ZIN.ld; rp.z_dtype = h->dtype;
+  rp.B = h->B; rp.A = h->A; rp.L = h->L; rp.seed = b->seed; rp.step = b->step; rp.sample0 = b->sample0;
+  rp.kl_scale = 1.0f / static_cast<float>(b->batch_global);
+  rp.kl_out = losses_ptr(h) + 3; rp.scratch = scratch_ptr(h, 0);
+  MFVAE_TRY(launch_reparam_kl_fwd(rp, s));
+  for (int l = 0; l < h->cfg.n_dec_hidden; ++l) MFVAE_TRY(run_gemm(h, h->g_dec_fwd[l], s));
+  MFVAE_TRY(run_gemm(h, h->g_sout_fwd, s));
+  MFVAE_TRY(run_gemm(h, h->g_rout_fwd, s));
+  MFVAE_TRY(run_gemm(h, h->g_rl_fwd, s));
+  if (out) {
+    out->d_recon_s = reinterpret_cast<const float*>(h->ws + h->RS.off); out->recon_s_ld = static_cast<int32_t>(h->RS.ld);
+    out->d_recon_r = reinterpret_cast<const float*>(h->ws + h->RR.off); out->recon_r_ld = static_cast<int32_t>(h->RR.ld);
+    out->d_latent = lat; out->d_losses = losses_ptr(h);
+  }
+  return 0;
+}
+
+static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStream_t s) {
+  MFVAE_TRY(check_ready(h, b));
+  MFVAE_CHECK(loss_kind >= MFVAE_LOSS_DEFAULT && loss_kind <= MFVAE_LOSS_JOINT_MSE, "unknown loss kind");
+  const int joint_mse = (loss_kind == MFVAE_LOSS_JOINT_MSE);
+  const int use_huber = (loss_kind == MFVAE_LOSS_DEFAULT) ? h->cfg.huber : (loss_kind == MFVAE_LOSS_HUBER);
+  MFVAE_CHECK(b->d_next && b->d_rew, "loss needs d_next and d_rew");
+  const double Bg = static_cast<double>(b->batch_global);
+  ReconLossArgs a{};
+  a.recon = reinterpret_cast<const float*>(h->ws + h->RS.off); a.recon_ld = h->RS.ld;
+  a.target = b->d_next; a.target_ld = h->S;
+  a.grad = h->ws + h->DRS.off; a.grad_ld = h->DRS.ld; a.grad_dtype = h->dtype;
+  a.B = h->B; a.width = h->S;
+  const double cs = joint_mse ? Bg * (h->S + h->A) : Bg * h->S;
+  const double cr = joint_mse ? Bg * (h->S + h->A) : Bg * h->A;
+  const float rw = joint_mse ? 1.0f : h->cfg.r_weight;
+  a.huber = joint_mse ? 0 : use_huber;
+  a.grad_scale = static_cast<float>(1.0 / cs); a.loss_scale = static_cast<float>(1.0 / cs);
+  a.loss_out = losses_ptr(h) + 1; a.scratch = scratch_ptr(h, 1);
+  MFVAE_TRY(launch_recon_loss(a, s));
+  a.recon = reinterpret_cast<const float*>(h->ws + h->RR.off); a.recon_ld = h->RR.ld;
+  a.target = b->d_rew; a.target_ld = h->A;
+  a.grad = h->ws + h->DRR.off; a.grad_ld = h->DRR.ld; a.width = h->A;
+  a.grad_scale = static_cast<float>(static_cast<double>(rw) / cr); a.loss_scale = static_cast<float>(1.0 / cr);
+  a.loss_out = losses_ptr(h) + 2; a.scratch = scratch_ptr(h, 2);
+  MFVAE_TRY(launch_recon_loss(a, s));
+  MFVAE_TRY(launch_loss_total(losses_ptr(h), rw, h->cfg.kl_weight, s));
+  return 0;
+}
+
+static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, const float* glat = nullptr, bool with_kl = true) {
+  MFVAE_TRY(check_ready(h, b));
+  const int dt = h->dtype, A = h->A, nh = h->cfg.n_dec_hidden;
+  float* G = h->ar.d_grad;
+  char* ws = h->ws;
+  // optimizer.zero_grad(): split-K wgrads and bias column sums accumulate with fp32 atomics
+  MFVAE_CUDA(cudaMemsetAsync(G, 0, static_cast<size_t>(h->arena_elems) * sizeof(float), s));
+  // reward_linear + output layers
+  MFVAE_TRY(run_gemm(h, h->g_rl_wg, s));
+  MFVAE_TRY(launch_colsum(ws + h->DRR.off, dt, 1, h->B, A, h->DRR.ld, 0, G + h->rlb.off, 0, s));
+  MFVAE_TRY(run_gemm(h, h->g_rl_dg, s));
+  MFVAE_TRY(run_gemm(h, h->g_rout_wg, s));
+  MFVAE_TRY(launch_colsum(ws + h->DRR0.off, dt, 1, h->B, A, h->DRR0.ld, 0, G + h->rOutB.off, 0, s));
+  MFVAE_TRY(run_gemm(h, h->g_rout_dg, s));
+  MFVAE_TRY(run_gemm(h, h->g_sout_wg, s));
+  MFVAE_TRY(launch_colsum(ws + h->DRS.off, dt, 1, h->B, h->S, h->DRS.ld, 0, G + h->sOutB.off, 0, s));
+  MFVAE_TRY(run_gemm(h, h->g_sout_dg, s));
+  MFVAE_CUDA(cudaEventRecord(h->buckets[0].ev, s));
+  // decoder hidden layers, last to first
+  for (int l = nh - 1; l >= 0; --l) {
+    MFVAE_TRY(run_gemm(h, h->g_dec_wg[l], s));
+    MFVAE_TRY(launch_colsum(ws + h->DHD[l].off, dt, 1, h->B, 2 * h->decH[l], h->DHD[l].ld, 0, G + h->decB[l].off, 0, s));
+    if (l == 1 || (l == 0 && nh == 1)) {}
+    MFVAE_TRY(run_gemm(h, h->g_dec_dg[l], s));
+    if (l == 1) MFVAE_CUDA(cudaEventRecord(h->buckets[1].ev, s));
+  }
+  if (nh == 1) MFVAE_CUDA(cudaEventRecord(h->buckets[1].ev, s));
+  MFVAE_CUDA(cudaEventRecord(h->buckets[2].ev, s));
+  // action tables (model.py:121: unregistered; gradients still flow)
+  MFVAE_TRY(launch_act_table_grad(ws + h->GZIN.off, dt, h->GZIN.ld, A * h->L, b->d_act, A, h->d_meta + 2 * A, A, h->C, h->B,
+                                  G + h->actT.off, static_cast<int64_t>(h->nact_max) * h->C, s));
+  // reparameterization + KL backward
+  ReparamBwdArgs rb{};
+  const float* lat = reinterpret_cast<const float*>(ws + h->LAT.off);
+  rb.gz = ws + h->GZIN.off; rb.gz_ld = h->GZIN.ld; rb.g_dtype = dt;
+  rb.mu = lat; rb.lv = lat + h->L; rb.lat_as = h->LAT.gs; rb.lat_bs = h->LAT.ld;
+  rb.eps = b->d_eps; rb.eps_ld = static_cast<int64_t>(A) * h->L;
+  rb.dlat = ws + h->DLAT.off; rb.dlat_as = h->DLAT.gs; rb.dlat_bs = h->DLAT.ld; rb.d_dtype = dt;
+  rb.B = h->B; rb.A = A; rb.L = h->L; rb.seed = b->seed; rb.step = b->step; rb.sample0 = b->sample0;
+  rb.kl_scale = with_kl ? h->cfg.kl_weight / static_cast<float>(b->batch_global) : 0.f;
+  rb.glat = glat;
+  MFVAE_TRY(launch_reparam_kl_bwd(rb, s));
+  // encoders, last layer to first
+  for (int l = h->ne - 1; l >= 0; --l) {
+    const MfvaeHandle_::Buf& D = (l + 1 == h->ne) ? h->DLAT : h->DXE[l];
+    MFVAE_TRY(run_gemm(h, h->g_enc_wg[l], s));
+    MFVAE_TRY(launch_colsum(ws + D.off, dt, A, h->B, h->encN[l], D.ld, D.gs, G + h->encB[l].off, h->encN[l], s));
+    MFVAE_TRY(run_gemm(h, h->g_enc_dg[l], s));
+  }
+  // id embedding (model.py:113,142)
+  if (b->d_idx)
+    MFVAE_TRY(launch_idx_emb_scatter(ws + h->GX0.off, dt, h->GX0.gs, h->GX0.ld, b->d_idx, A, A, h->I, h->B, G + h->idx_emb.off, s));
+  else
+    MFVAE_TRY(launch_colsum(ws + h->GX0.off, dt, A, h->B, h->I, h->GX0.ld, h->GX0.gs, G + h->idx_emb.off, h->I, s));
+  for (size_t i = 3; i < h->buckets.size(); ++i) MFVAE_CUDA(cudaEventRecord(h->buckets[i].ev, s));
+  return 0;
+}
+
+}  // namespace mfvae
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* mfvae_last_error(void) { return g_last_error.c_str(); }
+int mfvae_version(void) { return 100; }
+
+int mfvae_create(const MfvaeConfig* cfg, int device, MfvaeHandle* out) {
+  MFVAE_CHECK(cfg && out, "null argument");
+  MFVAE_CHECK(cfg->obs_dim && cfg->n_act, "config needs obs_dim and n_act");
+  if (device >= 0) {
+    int ndev = 0;
+    MFVAE_CUDA(cudaGetDeviceCount(&ndev));
+    MFVAE_CHECK(device < ndev, "no such CUDA device (this library has no CPU path)");
+    MFVAE_CUDA(cudaSetDevice(device));
+  }
+  MfvaeHandle_* h = new MfvaeHandle_();
+  h->cfg = *cfg; h->device = device;
+  h->obs_dim.assign(cfg->obs_dim, cfg->obs_dim + cfg->n_agents);
+  h->n_act.assign(cfg->n_act, cfg->n_act + cfg->n_agents);
+  h->cfg.obs_dim = h->obs_dim.data(); h->cfg.n_act = h->n_act.data();
+  if (build_layout(h) != 0) { delete h; return 1; }
+  if (device < 0) { *out = h; return 0; }        // layout-only handle
+  std::vector<int32_t> meta;
+  meta.insert(meta.end(), h->obs_off.begin(), h->obs_off.end());
+  meta.insert(meta.end(), h->obs_dim.begin(), h->obs_dim.end());
+  meta.insert(meta.end(), h->n_act.begin(), h->n_act.end());
+  if (cudaMalloc(&h->d_meta, meta.size() * sizeof(int32_t)) != cudaSuccess ||
+      cudaMemcpy(h->d_meta, meta.data(), meta.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+    delete h; MFVAE_FAIL("cudaMalloc / cudaMemcpy of the agent table failed");
+  }
+  // buckets in backward-completion order
+  auto add_bucket = [&](int64_t b, int64_t e) {
+    MfvaeHandle_::Bucket k{b, e, nullptr};
+    cudaEventCreateWithFlags(&k.ev, cudaEventDisableTiming);
+    h->buckets.push_back(k);
+  };
+  const int64_t l1 = (h->cfg.n_dec_hidden > 1) ? h->decW[1].off : h->reg3_begin;
+  add_bucket(h->reg3_begin, h->enc_begin);           // output layers + reward_linear
+  add_bucket(l1, h->reg3_begin);                      // decoder hidden layers >= 1 (may be empty)
+  add_bucket(h->reg2_begin, l1);                      // decoder layer 0 (largest)
+  add_bucket(0, h->reg2_begin);                       // idx_emb
+  if (h->cfg.optimize_encoders) add_bucket(h->enc_begin, h->arena_elems);
+  *out = h;
+  return 0;
+}
+
+int mfvae_destroy(MfvaeHandle h) {
+  if (!h) return 0;
+  free_plans(h);
+  for (auto& b : h->buckets) if (b.ev) cudaEventDestroy(b.ev);
+  if (h->d_meta) cudaFree(h->d_meta);
+  delete h;
+  return 0;
+}
+
+int64_t mfvae_arena_elems(MfvaeHandle h) { return h ? h->arena_elems : -1; }
+int64_t mfvae_optimized_elems(MfvaeHandle h) { return h ? h->optimized_elems : -1; }
+int32_t mfvae_tensor_count(MfvaeHandle h) { return h ? static_cast<int32_t>(h->table.size()) : -1; }
+
+int mfvae_tensor_table(MfvaeHandle h, MfvaeTensorInfo* out, int32_t capacity) {
+  MFVAE_CHECK(h && out, "null argument");
+  MFVAE_CHECK(capacity >= static_cast<int32_t>(h->table.size()), "tensor table capacity too small");
+  std::copy(h->table.begin(), h->table.end(), out);
+  return 0;
+}
+
+int mfvae_bind_arenas(MfvaeHandle h, const MfvaeArenas* a) {
+  MFVAE_CHECK(h && a, "null argument");
+  MFVAE_CHECK(h->device >= 0, "layout-only handle: there is no CPU path");
+  MFVAE_CHECK(a->d_param && a->d_grad && a->d_m && a->d_v, "param / grad / m / v arenas are required");
+  MFVAE_CHECK(h->dtype != kBF16 || a->d_shadow_bf16, "bf16 precision needs the bf16 shadow arena");
+  MFVAE_CHECK(reinterpret_cast<uintptr_t>(a->d_param) % 256 == 0 && reinterpret_cast<uintptr_t>(a->d_grad) % 256 == 0 &&
+              reinterpret_cast<uintptr_t>(a->d_shadow_bf16) % 256 == 0, "arenas must be 256-byte aligned");
+  h->ar = *a;
+  if (h->ws) return build_ops(h);
+  return 0;
+}
+
+int mfvae_refresh_shadow(MfvaeHandle h, void* stream) {
+  MFVAE_CHECK(h, "null handle");
+  if (!h->ar.d_shadow_bf16) return 0;
+  return launch_cast_bf16(h->ar.d_param, static_cast<__nv_bfloat16*>(h->ar.d_shadow_bf16), h->arena_elems,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int64_t mfvae_workspace_bytes(MfvaeHandle h, int32_t batch) {
+  if (!h || batch < 1) return -1;
+  MfvaeHandle_ tmp = *h;            // layout only; does not touch plans
+  tmp.tc.clear(); tmp.gemms.clear();
+  return layout_workspace(&tmp, batch);
+}
+
+int mfvae_bind_workspace(MfvaeHandle h, void* d_ws, int64_t bytes, int32_t batch) {
+  MFVAE_CHECK(h && d_ws, "null argument");
+  MFVAE_CHECK(h->device >= 0, "layout-only handle: there is no CPU path");
+  MFVAE_CHECK(batch >= 1, "batch must be positive");
+  MFVAE_CHECK(reinterpret_cast<uintptr_t>(d_ws) % 256 == 0, "workspace must be 256-byte aligned");
+  const int64_t need = layout_workspace(h, batch);
+  MFVAE_CHECK(bytes >= need, "workspace too small");
+  h->ws = static_cast<char*>(d_ws); h->ws_bytes = bytes; h->B = batch;
+  // scalar slots and tickets start at zero
+  MFVAE_CUDA(cudaMemset(h->ws + h->off_losses, 0, 64 * sizeof(float)));
+  MFVAE_CUDA(cudaMemset(h->ws + h->off_scratch, 0, 3 * 4096 * sizeof(float)));
+  if (h->ar.d_param) return build_ops(h);
+  return 0;
+}
+
+int mfvae_forward(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* stream) {
+  MFVAE_CHECK(h, "null handle");
+  return do_forward(h, b, out, static_cast<cudaStream_t>(stream));
+}
+int mfvae_loss(MfvaeHandle h, const MfvaeBatch* b, int32_t loss_kind, void* stream) {
+  MFVAE_CHECK(h, "null handle");
+  return do_loss(h, b, loss_kind, static_cast<cudaStream_t>(stream));
+}
+int mfvae_set_loss_weights(MfvaeHandle h, float kl_weight, float r_weight) {
+  MFVAE_CHECK(h, "null handle");
+  h->cfg.kl_weight = kl_weight; h->cfg.r_weight = r_weight;
+  return 0;
+}
+int mfvae_backward(MfvaeHandle h, const MfvaeBatch* b, void* stream) {
+  MFVAE_CHECK(h, "null handle");
+  return do_backward(h, b, static_cast<cudaStream_t>(stream));
+}
+int mfvae_backward_ext(MfvaeHandle h, const MfvaeBatch* b, const float* d_g_recon_s, int64_t ld_s,
+                       const float* d_g_recon_r, int64_t ld_r, const float* d_g_latent, void* stream) {
+  MFVAE_CHECK(h, "null handle");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MFVAE_TRY(check_ready(h, b));
+  MFVAE_TRY(launch_cast2d(d_g_recon_s, ld_s, h->ws + h->DRS.off, h->DRS.ld, h->dtype, h->B, h->S, s));
+  MFVAE_TRY(launch_cast2d(d_g_recon_r, ld_r, h->ws + h->DRR.off, h->DRR.ld, h->dtype, h->B, h->A, s));
+  return do_backward(h, b, s, d_g_latent, false);
+}
+int mfvae_fwd_bwd(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* stream) {
+  MFVAE_CHECK(h, "null handle");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MFVAE_TRY(do_forward(h, b, out, s));
+  MFVAE_TRY(do_loss(h, b, MFVAE_LOSS_DEFAULT, s));
+  return do_backward(h, b, s);
+}
+
+int mfvae_adam_step(MfvaeHandle h, float lr, float beta1, float beta2, float eps, int64_t t, void* stream) {
+  MFVAE_CHECK(h && h->ar.d_param, "arenas are not bound");
+  return launch_adam(h->ar.d_param, h->ar.d_grad, h->ar.d_m, h->ar.d_v,
+                     static_cast<__nv_bfloat16*>(h->ar.d_shadow_bf16), h->optimized_elems, lr, beta1, beta2, eps, t,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int32_t mfvae_bucket_count(MfvaeHandle h) { return h ? static_cast<int32_t>(h->buckets.size()) : -1; }
+int mfvae_bucket(MfvaeHandle h, int32_t i, int64_t* begin, int64_t* end, void** event) {
+  MFVAE_CHECK(h && i >= 0 && i < static_cast<int32_t>(h->buckets.size()), "bucket index out of range");
+  if (begin) *begin = h->buckets[i].begin;
+  if (end) *end = h->buckets[i].end;
+  if (event) *event = h->buckets[i].ev;
+  return 0;
+}
+int mfvae_bucket_wait(MfvaeHandle h, int32_t i, void* stream) {
+  MFVAE_CHECK(h && i >= 0 && i < static_cast<int32_t>(h->buckets.size()), "bucket index out of range");
+  MFVAE_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->buckets[i].ev, 0));
+  return 0;
+}
+
+// ---- standalone kernels ---------------------------------------------------------------------------
+int mfvae_reparam_kl(const float* d_mu, const float* d_logvar, const float* d_eps_or_null, void* d_z, int32_t z_dtype,
+                     int64_t batch, int32_t width, uint64_t seed, uint64_t step, int64_t sample0, int64_t batch_global,
+                     float* d_kl_out, float* d_scratch, void* stream) {
+  MFVAE_CHECK(d_mu && d_logvar && d_z && d_kl_out && d_scratch, "null argument");
+  ReparamArgs a{};
+  a.mu = d_mu; a.lv = d_logvar; a.lat_as = width; a.lat_bs = width;   // one "agent" of width A*L
+  a.eps = d_eps_or_null; a.eps_ld = width; a.z = d_z; a.z_ld = width; a.z_dtype = z_dtype;
+  a.B = batch; a.A = 1; a.L = width; a.seed = seed; a.step = step; a.sample0 = sample0;
+  a.kl_scale = 1.0f / static_cast<float>(batch_global); a.kl_out = d_kl_out; a.scratch = d_scratch;
+  return launch_reparam_kl_fwd(a, static_cast<cudaStream_t>(stream));
+}
+
+int mfvae_recon_loss(const float* d_recon, int32_t recon_ld, const float* d_target, int32_t target_ld, void* d_grad,
+                     int32_t grad_ld, int32_t grad_dtype, int64_t batch, int32_t width, int32_t huber, float weight,
+                     int64_t count_global, float* d_loss_out, float* d_scratch, void* stream) {
+  MFVAE_CHECK(d_recon && d_target && d_loss_out && d_scratch, "null argument");
+  ReconLossArgs a{};
+  a.recon = d_recon; a.recon_ld = recon_ld; a.target = d_target; a.target_ld = target_ld;
+  a.grad = d_grad; a.grad_ld = grad_ld; a.grad_dtype = grad_dtype; a.B = batch; a.width = width; a.huber = huber;
+  a.grad_scale = static_cast<float>(static_cast<double>(weight) / static_cast<double>(count_global));
+  a.loss_scale = static_cast<float>(1.0 / static_cast<double>(count_global));
+  a.loss_out = d_loss_out; a.scratch = d_scratch;
+  return launch_recon_loss(a, static_cast<cudaStream_t>(stream));
+}
+
+int mfvae_adam_flat(float* d_p, const float* d_g, float* d_m, float* d_v, void* d_shadow, int64_t n, float lr,
+                    float beta1, float beta2, float eps, int64_t t, void* stream) {
+  MFVAE_CHECK(d_p && d_g && d_m && d_v, "null argument");
+  return launch_adam(d_p, d_g, d_m, d_v, static_cast<__nv_bfloat16*>(d_shadow), n, lr, beta1, beta2, eps, t,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int mfvae_philox_normal(float* d_out, int64_t batch, int32_t width, uint64_t seed, uint64_t step, int64_t sample0, void* stream) {
+  MFVAE_CHECK(d_out, "null argument");
+  return launch_philox_normal(d_out, batch, width, seed, step, sample0, static_cast<cudaStream_t>(stream));
+}
+
+int mfvae_gemm(int32_t engine, int32_t dtype, int32_t groups, int32_t M, int32_t N, int32_t K,
+               const void* d_A, int64_t a_gs, int64_t a_rs, int64_t a_cs,
+               const void* d_B, int64_t b_gs, int64_t b_rs, int64_t b_cs,
+               void* d_C, int64_t c_gs, int64_t c_ld, int32_t c_dtype,
+               const float* d_bias, int64_t bias_gs, int32_t epilogue,
+               const void* d_aux, int64_t aux_gs, int64_t aux_ld, int32_t split_k, void* stream) {
+  GemmOp o; o.G = groups; o.M = M; o.N = N; o.K = K; o.dtype = dtype;
+  o.A = d_A; o.a_gs = a_gs; o.a_rs = a_rs; o.a_cs = a_cs;
+  o.B = d_B; o.b_gs = b_gs; o.b_rs = b_rs; o.b_cs = b_cs;
+  o.C = d_C; o.c_gs = c_gs; o.c_ld = c_ld; o.c_dtype = c_dtype;
+  o.bias = d_bias; o.bias_gs = bias_gs; o.epi = epilogue; o.aux = d_aux; o.aux_gs = aux_gs; o.aux_ld = aux_ld;
+  o.split_k = split_k < 1 ? 1 : split_k;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (engine == MFVAE_ENGINE_AUTO) engine = (dtype == kBF16) ? MFVAE_ENGINE_TCGEN05 : MFVAE_ENGINE_SIMT;
+  if (engine == MFVAE_ENGINE_SIMT) return gemm_simt(o, s);
+  TcPlan* p = nullptr;
+  MFVAE_TRY(gemm_tc_plan(o, &p));
+  int r = gemm_tc_run(p, s);
+  if (r == 0 && cudaStreamSynchronize(s) != cudaSuccess) r = mfvae::fail(__FILE__, __LINE__, "tcgen05 GEMM failed at synchronize");
+  gemm_tc_free(p);
+  return r;
+}
+
+}  // extern "C"

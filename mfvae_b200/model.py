@@ -1,0 +1,578 @@
+"""Drop-in for the reference ``torch_ver/model.py`` on a B200.
+
+Same module-level names and call signatures as the reference (``/root/reference/torch_ver/model.py``):
+``kl_weight``, ``r_weight`` (:5-6), ``loss_vae_fn`` (:8), ``loss_s_r_vae_fn`` (:19), ``Encoder`` (:43),
+``ActionEncoder`` (:60), ``reparameterize`` (:77), ``Decoder`` (:84), ``MAVAE`` (:101) — but the arithmetic
+of ``MAVAE.forward``, the ELBO loss, the backward pass and the Adam update runs in hand-written sm_100a
+CUDA behind the C ABI of ``include/mfvae.h`` (``libmfvae_b200.so``).  There is no CPU / eager fallback:
+calling the model without a CUDA device raises.
+
+What stays host-side Python: packing the reference's dict-of-tensors inputs into the packed batch the
+kernels read, parameter bookkeeping (every ``nn.Parameter`` is a *view* into one flat fp32 arena, its
+``.grad`` a view into the gradient arena, so ``state_dict()`` / ``load_state_dict()`` / ``parameters()``
+behave as in the reference without copies), and the autograd bridge that lets the reference's own call
+sequence ``model(...) -> loss_s_r_vae_fn(...) -> loss.backward() -> optimizer.step()``
+(``torch_ver/main.py:87-97``) drive the engine.
+
+Reference quirks kept on purpose: the per-agent encoders and action tables live in
+plain dicts and are therefore not registered / not optimised (model.py:112,114) unless
+``optimize_encoders=True``; the never-called ``decoder`` (model.py:127) exists and appears in
+``state_dict()``; outputs are ``(recon_state, recon_reward, mu_all: list, log_var_all: list)``.
+"""
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+kl_weight = 0.0025
+r_weight = 0.005
+
+_ENC_HIDDEN = (64, 64, 256)
+_DEC_HIDDEN = (1024, 256, 64, 256, 1024)
+
+
+# ----------------------------------------------------------------------------------------------
+# small torch modules with the reference's attribute layout (``.net`` = Sequential of Linear / ReLU)
+# ----------------------------------------------------------------------------------------------
+def _sequential(widths: Sequence[int], device=None) -> nn.Sequential:
+    mods: List[nn.Module] = []
+    for i in range(len(widths) - 1):
+        mods.append(nn.Linear(widths[i], widths[i + 1], device=device))
+        if i + 2 < len(widths):
+            mods.append(nn.ReLU())
+    return nn.Sequential(*mods)
+
+
+class _MLP(nn.Module):
+    HIDDEN: Sequence[int] = ()
+
+    def __init__(self, in_dim, out_dim, hidden=None, device=None):
+        super().__init__()
+        hidden = tuple(self.HIDDEN if hidden is None else hidden)
+        self.net = _sequential((in_dim, *hidden, out_dim), device=device)
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class Encoder(_MLP):
+    """in -> 64 -> 64 -> 256 -> out (reference model.py:43-57)."""
+    HIDDEN = _ENC_HIDDEN
+
+
+class ActionEncoder(_MLP):
+    """in -> 64 -> out, continuous-action variant (reference model.py:60-74)."""
+    HIDDEN = (64,)
+
+
+class Decoder(_MLP):
+    """in -> 1024 -> 256 -> 64 -> 256 -> 1024 -> out (reference model.py:84-98)."""
+    HIDDEN = _DEC_HIDDEN
+
+
+def reparameterize(mu, log_var):
+    """mu + eps * exp(log_var / 2) with eps ~ N(0, 1) (reference model.py:77-81); plain torch, kept for API
+    parity — ``MAVAE.forward`` draws its eps inside the fused CUDA kernel (counter-based Philox)."""
+    return mu + torch.randn_like(mu) * torch.exp(0.5 * log_var)
+
+
+# ----------------------------------------------------------------------------------------------
+# packed batch
+# ----------------------------------------------------------------------------------------------
+class PackedBatch:
+    """Device-resident batch in the layout the kernels read: what ``create_dataset``
+    (reference trainer.py:7-45) produces, without the per-agent dict indirection.
+
+    obs  [B, S] fp32   observations of all agents concatenated in codebook order
+    act  [B, A] fp32   float-coded discrete action per agent (replay_buffer.py:76)
+    next [B, S] fp32   next observations (= ``next_states`` target)      (optional)
+    rew  [B, A] fp32   rewards (= ``rewards`` target)                     (optional)
+    idx  [B, A] fp32   agent-index column of ``idx_state`` or None = codebook order
+    eps  [B, A*L] fp32 explicit normal draw or None = Philox(seed, step, sample0 + row)
+    """
+
+    def __init__(self, obs, act, next=None, rew=None, idx=None, eps=None, sample0=0, batch_global=None):
+        self.obs, self.act, self.next, self.rew, self.idx, self.eps = obs, act, next, rew, idx, eps
+        self.sample0 = int(sample0)
+        self.batch_global = int(batch_global if batch_global is not None else obs.shape[0])
+
+    @property
+    def batch(self):
+        return self.obs.shape[0]
+
+
+def _f32c(t, device):
+    return t.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd bridge
+# ----------------------------------------------------------------------------------------------
+class _ForwardFn(torch.autograd.Function):
+    """Outputs of the CUDA forward as autograd nodes: any torch loss built on them back-propagates into
+    ``mfvae_backward_ext``."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, recon_s, recon_r, latent):
+        ctx.model = model
+        ctx.serial = model._serial
+        return recon_s.view_as(recon_s), recon_r.view_as(recon_r), latent.view_as(latent)
+
+    @staticmethod
+    def backward(ctx, g_rs, g_rr, g_lat):
+        m = ctx.model
+        if ctx.serial != m._serial:
+            raise RuntimeError("mfvae_b200: backward through a stale forward (the engine keeps one batch of activations)")
+        m._backward_ext(g_rs, g_rr, g_lat)
+        return None, None, None, None, None
+
+
+class _FusedLossFn(torch.autograd.Function):
+    """The fused ELBO: values come from ``mfvae_loss``; ``backward`` runs ``mfvae_backward``."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, losses):
+        ctx.model = model
+        ctx.serial = model._serial
+        return losses[0].clone(), losses[1].clone(), losses[2].clone(), losses[3].clone()
+
+    @staticmethod
+    def backward(ctx, g0, g1, g2, g3):
+        m = ctx.model
+        if ctx.serial != m._serial:
+            raise RuntimeError("mfvae_b200: backward through a stale forward (the engine keeps one batch of activations)")
+        m._backward_fused()
+        return None, None, None
+
+
+def _owner(t):
+    return getattr(t, "_mfvae_owner", None)
+
+
+def loss_s_r_vae_fn(recon_s, recon_r, s_hat, r_hat, mean_all, logvar_all, device, using_huber_loss=True):
+    """Reference model.py:19-40.  When the reconstructions come straight from a ``MAVAE`` of this package the
+    fused CUDA loss (+ gradient seeds) is used; otherwise (e.g. ``Trainer.training_model``'s denormalised
+    rewards) the same formula is evaluated with torch ops and autograd flows into ``mfvae_backward_ext``."""
+    m = _owner(recon_s)
+    if (m is not None and m is _owner(recon_r) and getattr(recon_s, "_mfvae_serial", -1) == m._serial
+            and getattr(recon_r, "_mfvae_serial", -2) == m._serial and mean_all is m._last_mu
+            and logvar_all is m._last_lv and torch.is_grad_enabled()):
+        return m._fused_loss(s_hat, r_hat, L.LOSS_HUBER if using_huber_loss else L.LOSS_MSE)
+    F = torch.nn.functional
+    s_hat = s_hat.to(device); r_hat = r_hat.to(device)
+    recon_s = recon_s.to(device); recon_r = recon_r.to(device)
+    fn = F.huber_loss if using_huber_loss else F.mse_loss
+    s_loss = fn(s_hat, recon_s)
+    rr_loss = fn(r_hat, recon_r)
+    kl = _kl_sum_of_means(mean_all, logvar_all)
+    loss = s_loss + rr_loss * r_weight + kl * kl_weight
+    return loss, s_loss, rr_loss, kl
+
+
+def loss_vae_fn(y, y_hat, mean_all, logvar_all, device):
+    """Reference model.py:8-16 (joint MSE over [next_state | reward] + KL).  Legacy, torch ops + autograd bridge."""
+    y = y.to(device); y_hat = y_hat.to(device)
+    return torch.nn.functional.mse_loss(y_hat, y) + _kl_sum_of_means(mean_all, logvar_all) * kl_weight
+
+
+def _kl_sum_of_means(mean_all, logvar_all):
+    kl = 0.0
+    for mu, lv in zip(mean_all, logvar_all):
+        kl = kl + torch.mean(-0.5 * torch.sum(1 + lv - mu ** 2 - torch.exp(lv), 1), 0)
+    return kl
+
+
+# ----------------------------------------------------------------------------------------------
+# the model
+# ----------------------------------------------------------------------------------------------
+class MAVAE(nn.Module):
+    """Reference ctor signature (model.py:102) plus keyword-only engine options."""
+
+    def __init__(self, idx_features: int, obs_features: int, action_features: int, descrete_act: bool,
+                 agents: list, obs_dim: dict, action_dim: dict, device: str, *,
+                 precision: str = "bf16", engine: str = "auto", enc_hidden: Optional[Sequence[int]] = None,
+                 dec_hidden: Optional[Sequence[int]] = None, optimize_encoders: bool = False,
+                 include_dead_decoder: bool = True, seed: int = 0x5EED, huber: bool = True):
+        super().__init__()
+        if not descrete_act:
+            raise NotImplementedError("continuous-action ActionEncoder path (model.py:123,148) is not built yet")
+        self.obs_dim = obs_dim
+        self.act_dim = action_dim
+        self.feature = obs_features
+        self.device = device
+        self.descrete_act = descrete_act
+        self.agents = list(agents)
+        self.idx_features, self.action_features = idx_features, action_features
+        self.enc_hidden = tuple(_ENC_HIDDEN if enc_hidden is None else enc_hidden)
+        self.dec_hidden = tuple(_DEC_HIDDEN if dec_hidden is None else dec_hidden)
+        self.precision = precision
+        self.optimize_encoders = bool(optimize_encoders)
+        self.philox_seed = int(seed)
+        self.philox_step = 0
+        self.data_parallel = False          # set by Trainer / enable_data_parallel()
+        self._pg = None
+
+        tdev = torch.device(device)
+        self._tdev = tdev
+        A = len(self.agents)
+        cfg = L.MfvaeConfig()
+        cfg.n_agents, cfg.idx_features, cfg.latent, cfg.act_features = A, idx_features, obs_features, action_features
+        cfg.n_enc_hidden = len(self.enc_hidden)
+        cfg.n_dec_hidden = len(self.dec_hidden)
+        for i, w in enumerate(self.enc_hidden):
+            cfg.enc_hidden[i] = w
+        for i, w in enumerate(self.dec_hidden):
+            cfg.dec_hidden[i] = w
+        self._obs_arr = (C.c_int32 * A)(*[int(obs_dim[a]) for a in self.agents])
+        self._act_arr = (C.c_int32 * A)(*[int(action_dim[a]) for a in self.agents])
+        cfg.obs_dim = C.cast(self._obs_arr, C.POINTER(C.c_int32))
+        cfg.n_act = C.cast(self._act_arr, C.POINTER(C.c_int32))
+        cfg.kl_weight, cfg.r_weight, cfg.huber = kl_weight, r_weight, int(huber)
+        cfg.precision = {"fp32": L.PREC_FP32, "bf16": L.PREC_BF16}[precision]
+        cfg.engine = {"auto": L.ENGINE_AUTO, "simt": L.ENGINE_SIMT, "tcgen05": L.ENGINE_TCGEN05}[engine]
+        cfg.optimize_encoders = int(self.optimize_encoders)
+        self._cfg = cfg
+        lib = L.lib()
+        self._h = C.c_void_p()
+        dev_index = -1 if tdev.type != "cuda" else (tdev.index if tdev.index is not None else torch.cuda.current_device())
+        L.check(lib.mfvae_create(C.byref(cfg), dev_index, C.byref(self._h)))
+        self._on_gpu = dev_index >= 0
+
+        # ---- arenas: one flat tensor each; parameters are views ----
+        n = lib.mfvae_arena_elems(self._h)
+        self._n_opt = lib.mfvae_optimized_elems(self._h)
+        self._arena = torch.zeros(n, dtype=torch.float32, device=tdev)
+        self._grad = torch.zeros(n, dtype=torch.float32, device=tdev)
+        self._m = torch.zeros(n, dtype=torch.float32, device=tdev)
+        self._v = torch.zeros(n, dtype=torch.float32, device=tdev)
+        self._shadow = torch.zeros(n, dtype=torch.bfloat16, device=tdev) if precision == "bf16" else None
+        self._adam_t = 0
+        nt = lib.mfvae_tensor_count(self._h)
+        table = (L.MfvaeTensorInfo * nt)()
+        L.check(lib.mfvae_tensor_table(self._h, table, nt))
+        self._table = list(table)
+        if self._on_gpu:
+            ar = L.MfvaeArenas(L.ptr(self._arena), L.ptr(self._grad), L.ptr(self._m), L.ptr(self._v), L.ptr(self._shadow))
+            L.check(lib.mfvae_bind_arenas(self._h, C.byref(ar)))
+
+        self._views: List[tuple] = []          # (parameter, grad view)
+        self._build_modules(include_dead_decoder)
+        self.reset_parameters()
+
+        self._ws = None
+        self._ws_batch = -1
+        self._serial = 0
+        self._arena_version = -1
+        self._anchor = torch.zeros(1, device=tdev, requires_grad=True)
+        self._cur: Optional[PackedBatch] = None
+        self._cb = None
+        self._last_mu = self._last_lv = None
+        self._comm_stream = None
+
+    # ------------------------------------------------------------------ construction helpers
+    def _view(self, info, arena):
+        v = arena[info.offset: info.offset + info.rows * info.ld].view(info.rows, info.ld)
+        if info.cols != info.ld:
+            v = v[:, :info.cols]
+        return v
+
+    def _param(self, info, squeeze=False):
+        v, g = self._view(info, self._arena), self._view(info, self._grad)
+        if squeeze:
+            v, g = v[0], g[0]
+        p = nn.Parameter(v)
+        p.grad = g
+        self._views.append((p, g))
+        return p
+
+    def _arena_linear(self, w_info, b_info):
+        lin = nn.Linear(w_info.cols, w_info.rows, device="meta")
+        lin.weight = self._param(w_info)
+        lin.bias = self._param(b_info, squeeze=True)
+        return lin
+
+    def _arena_mlp(self, cls, infos):
+        """cls instance whose ``.net`` Linear layers are arena views; infos = [(w, b), ...]."""
+        obj = cls.__new__(cls)
+        nn.Module.__init__(obj)
+        mods = []
+        for i, (w, b) in enumerate(infos):
+            mods.append(self._arena_linear(w, b))
+            if i + 1 < len(infos):
+                mods.append(nn.ReLU())
+        obj.net = nn.Sequential(*mods)
+        return obj
+
+    def _build_modules(self, include_dead_decoder):
+        by = {}
+        for t in self._table:
+            by[(t.kind, t.agent, t.layer)] = t
+        A = len(self.agents)
+        ne, nd = len(self.enc_hidden) + 1, len(self.dec_hidden) + 1
+        self.encoders = {}
+        self.idx_emb = nn.Embedding(A, self.idx_features, device="meta")
+        self.idx_emb.weight = self._param(by[(L.T_IDX_EMB, -1, -1)])
+        self.action_encoder = {}
+        for ai, a in enumerate(self.agents):
+            self.encoders[a] = self._arena_mlp(Encoder, [(by[(L.T_ENC_W, ai, l)], by[(L.T_ENC_B, ai, l)]) for l in range(ne)])
+            t = by[(L.T_ACT_TABLE, ai, -1)]
+            emb = nn.Embedding(t.rows, t.cols, device="meta")
+            emb.weight = self._param(t)
+            self.action_encoder[a] = emb
+        S = sum(int(self.obs_dim[a]) for a in self.agents)
+        din = (self.feature + self.action_features) * A
+        if include_dead_decoder:   # model.py:127 — constructed, registered, never called
+            self.decoder = Decoder(din, S + A, hidden=self.dec_hidden, device=self._tdev)
+        self.state_decoder = self._arena_mlp(Decoder, [(by[(L.T_SDEC_W, -1, l)], by[(L.T_SDEC_B, -1, l)]) for l in range(nd)])
+        self.reward_decoder = self._arena_mlp(Decoder, [(by[(L.T_RDEC_W, -1, l)], by[(L.T_RDEC_B, -1, l)]) for l in range(nd)])
+        self.reward_linear = self._arena_linear(by[(L.T_RLIN_W, -1, -1)], by[(L.T_RLIN_B, -1, -1)])
+        if self.optimize_encoders:      # extension: make the per-agent nets visible to parameters()
+            self._extra = nn.ModuleList(list(self.encoders.values()) + list(self.action_encoder.values()))
+
+    @torch.no_grad()
+    def reset_parameters(self):
+        """torch default initialisers (what the reference gets from nn.Linear / nn.Embedding) +
+        reward_linear = ones / zeros (model.py:131-132)."""
+        for p, _ in self._views:
+            p.zero_()
+        def init_linear(lin):
+            nn.init.kaiming_uniform_(lin.weight, a=math.sqrt(5))
+            bound = 1.0 / math.sqrt(lin.weight.shape[1])
+            nn.init.uniform_(lin.bias, -bound, bound)
+        nn.init.normal_(self.idx_emb.weight)
+        for a in self.agents:
+            for mod in self.encoders[a].net:
+                if isinstance(mod, nn.Linear):
+                    init_linear(mod)
+            nn.init.normal_(self.action_encoder[a].weight)
+        for dec in (self.state_decoder, self.reward_decoder):
+            for mod in dec.net:
+                if isinstance(mod, nn.Linear):
+                    init_linear(mod)
+        nn.init.ones_(self.reward_linear.weight)
+        nn.init.zeros_(self.reward_linear.bias)
+
+    def named_arena_tensors(self) -> Dict[str, torch.Tensor]:
+        """Every arena-backed tensor under the oracle's naming (encoders.<agent>.net.<i>.weight, ...)."""
+        out = {"idx_emb.weight": self.idx_emb.weight}
+        for a in self.agents:
+            for n, p in self.encoders[a].named_parameters():
+                out[f"encoders.{a}.{n}"] = p
+            out[f"action_encoder.{a}.weight"] = self.action_encoder[a].weight
+        for pre in ("state_decoder", "reward_decoder", "reward_linear"):
+            for n, p in getattr(self, pre).named_parameters():
+                out[f"{pre}.{n}"] = p
+        return out
+
+    @torch.no_grad()
+    def load_named(self, tensors: Dict[str, torch.Tensor]):
+        mine = self.named_arena_tensors()
+        for k, p in mine.items():
+            p.copy_(tensors[k].to(p.device, torch.float32))
+        if hasattr(self, "decoder"):
+            for n, p in self.decoder.named_parameters():
+                k = f"decoder.{n}"
+                if k in tensors:
+                    p.copy_(tensors[k].to(p.device, torch.float32))
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                L.lib().mfvae_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self._tdev).cuda_stream)
+
+    def _require_gpu(self):
+        if not self._on_gpu:
+            raise RuntimeError("mfvae_b200: MAVAE was created on a non-CUDA device; the hot path has no CPU fallback")
+
+    def _bind(self, B):
+        if B == self._ws_batch:
+            return
+        lib = L.lib()
+        need = lib.mfvae_workspace_bytes(self._h, B)
+        if need <= 0:
+            raise RuntimeError("mfvae_b200: bad batch size")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.zeros(need, dtype=torch.uint8, device=self._tdev)
+        torch.cuda.current_stream(self._tdev).synchronize()
+        L.check(lib.mfvae_bind_workspace(self._h, L.ptr(self._ws), self._ws.numel(), B))
+        self._ws_batch = B
+
+    def _sync_shadow(self):
+        """Parameter views share the arena's version counter: any in-place edit (optimizer, load_state_dict,
+        POP-ART rescale) bumps it and the bf16 shadow is refreshed before the next forward."""
+        if self._shadow is None:
+            return
+        v = self._arena._version
+        if v != self._arena_version:
+            L.check(L.lib().mfvae_refresh_shadow(self._h, self._stream()))
+            self._arena_version = v
+
+    def _cbatch(self, pb: PackedBatch):
+        cb = L.MfvaeBatch()
+        cb.d_obs, cb.d_act = pb.obs.data_ptr(), pb.act.data_ptr()
+        cb.d_next = pb.next.data_ptr() if pb.next is not None else None
+        cb.d_rew = pb.rew.data_ptr() if pb.rew is not None else None
+        cb.d_idx = pb.idx.data_ptr() if pb.idx is not None else None
+        cb.d_eps = pb.eps.data_ptr() if pb.eps is not None else None
+        cb.batch, cb.sample0, cb.batch_global = pb.batch, pb.sample0, pb.batch_global
+        cb.seed, cb.step = self.philox_seed, self.philox_step
+        return cb
+
+    def _ws_view(self, ptr, rows, ld, cols):
+        off = ptr - self._ws.data_ptr()
+        t = self._ws[off: off + rows * ld * 4].view(torch.float32).view(rows, ld)
+        return t[:, :cols] if cols != ld else t
+
+    def pack(self, idx_state: dict, actions: dict, eps=None) -> PackedBatch:
+        """dict-of-tensors inputs of the reference forward -> PackedBatch on the device."""
+        keys = list(idx_state.keys())
+        if keys != self.agents:
+            raise NotImplementedError("idx_state must list the agents in the model's agent order")
+        dev = self._tdev
+        cols = [_f32c(idx_state[a], dev) for a in keys]
+        obs = torch.cat([c[:, 1:] for c in cols], dim=1)
+        idx = torch.stack([c[:, 0] for c in cols], dim=1).contiguous()
+        act = torch.cat([_f32c(actions[a], dev).reshape(-1, 1) for a in keys], dim=1)
+        if eps is not None:
+            eps = _f32c(eps, dev)
+        return PackedBatch(obs, act, idx=idx, eps=eps)
+
+    def forward(self, idx_state, actions=None, eps=None):
+        """Reference signature ``forward(idx_state: dict, actions: dict)``; a ``PackedBatch`` may be passed as
+        the first argument instead.  ``eps`` ([B, A*L]) overrides the Philox draw (parity tests)."""
+        self._require_gpu()
+        pb = idx_state if isinstance(idx_state, PackedBatch) else self.pack(idx_state, actions, eps)
+        if pb.batch < 2:
+            # the reference's .squeeze() at model.py:159 makes B == 1 fail with a dimension error
+            raise RuntimeError("Tensors must have same number of dimensions (B == 1 is unsupported, as in the reference)")
+        lib = L.lib()
+        self._bind(pb.batch)
+        self._sync_shadow()
+        self._serial += 1
+        self._cur = pb
+        self._cb = self._cbatch(pb)
+        out = L.MfvaeOutputs()
+        L.check(lib.mfvae_forward(self._h, C.byref(self._cb), C.byref(out), self._stream()))
+        B, A, Lt = pb.batch, len(self.agents), self.feature
+        S = pb.obs.shape[1]
+        recon_s = self._ws_view(out.d_recon_s, B, out.recon_s_ld, S)
+        recon_r = self._ws_view(out.d_recon_r, B, out.recon_r_ld, A)
+        latent = self._ws_view(out.d_latent, A * B, 2 * Lt, 2 * Lt).view(A, B, 2 * Lt)
+        self._losses = self._ws_view(out.d_losses, 1, 4, 4)[0]
+        if torch.is_grad_enabled():
+            recon_s, recon_r, latent = _ForwardFn.apply(self._anchor, self, recon_s, recon_r, latent)
+        for t in (recon_s, recon_r):
+            t._mfvae_owner, t._mfvae_serial = self, self._serial
+        mu_all = [latent[a, :, :Lt] for a in range(A)]
+        lv_all = [latent[a, :, Lt:] for a in range(A)]
+        self._last_mu, self._last_lv = mu_all, lv_all
+        if self.training:
+            self.philox_step += 1
+        return recon_s, recon_r, mu_all, lv_all
+
+    # ------------------------------------------------------------------ loss / backward / optimizer
+    def _fused_loss(self, s_hat, r_hat, kind):
+        lib = L.lib()
+        pb = self._cur
+        pb.next = _f32c(s_hat, self._tdev)
+        pb.rew = _f32c(r_hat, self._tdev)
+        self._cb.d_next, self._cb.d_rew = pb.next.data_ptr(), pb.rew.data_ptr()
+        L.check(lib.mfvae_set_loss_weights(self._h, kl_weight, r_weight))
+        L.check(lib.mfvae_loss(self._h, C.byref(self._cb), kind, self._stream()))
+        return _FusedLossFn.apply(self._anchor, self, self._losses)
+
+    def _attach_grads(self):
+        for p, g in self._views:
+            if p.grad is not g:
+                p.grad = g
+
+    def _backward_fused(self):
+        L.check(L.lib().mfvae_backward(self._h, C.byref(self._cb), self._stream()))
+        self._after_backward()
+
+    def _backward_ext(self, g_rs, g_rr, g_lat):
+        def prep(g):
+            return None if g is None else g.to(torch.float32).contiguous()
+        g_rs, g_rr, g_lat = prep(g_rs), prep(g_rr), prep(g_lat)
+        L.check(L.lib().mfvae_backward_ext(self._h, C.byref(self._cb), L.ptr(g_rs), g_rs.shape[1] if g_rs is not None else 0,
+                                           L.ptr(g_rr), g_rr.shape[1] if g_rr is not None else 0, L.ptr(g_lat), self._stream()))
+        self._after_backward()
+
+    def _after_backward(self):
+        self._attach_grads()
+        if self.data_parallel:
+            self._allreduce_grads()
+
+    # ---- data parallel: bucketed all-reduce on a side stream, launched as each bucket's event fires ----
+    def enable_data_parallel(self, process_group=None):
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self._pg = process_group
+        self.data_parallel = dist.get_world_size(process_group) > 1
+        if self._on_gpu and self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(self._tdev)
+
+    def grad_buckets(self):
+        lib = L.lib()
+        out = []
+        for i in range(lib.mfvae_bucket_count(self._h)):
+            b, e = C.c_int64(), C.c_int64()
+            L.check(lib.mfvae_bucket(self._h, i, C.byref(b), C.byref(e), None))
+            if e.value > b.value:
+                out.append((i, b.value, e.value))
+        return out
+
+    def _allreduce_grads(self):
+        import torch.distributed as dist
+        lib = L.lib()
+        works = []
+        main = torch.cuda.current_stream(self._tdev)
+        with torch.cuda.stream(self._comm_stream):
+            for i, b, e in self.grad_buckets():
+                L.check(lib.mfvae_bucket_wait(self._h, i, C.c_void_p(self._comm_stream.cuda_stream)))
+                works.append(dist.all_reduce(self._grad[b:e], group=self._pg, async_op=True))
+            self._comm_stream.wait_stream(main)       # losses are final at the end of the main stream's queue
+            works.append(dist.all_reduce(self._losses, group=self._pg, async_op=True))
+        for w in works:
+            w.wait()
+        main.wait_stream(self._comm_stream)
+
+    def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8):
+        """Fused Adam over the registered (optimised) prefix of the arena; also refreshes the bf16 shadow."""
+        self._require_gpu()
+        self._adam_t += 1
+        L.check(L.lib().mfvae_adam_step(self._h, float(lr), float(betas[0]), float(betas[1]), float(eps), self._adam_t, self._stream()))
+
+    def train_step(self, pb: PackedBatch, lr: float, betas=(0.9, 0.999), eps=1e-8):
+        """Fast path: forward + fused ELBO + backward (+ all-reduce) + Adam, no autograd graph.
+        Returns the device tensor [loss, s_loss, r_loss, kl_loss]."""
+        self._require_gpu()
+        lib = L.lib()
+        self._bind(pb.batch)
+        self._sync_shadow()
+        self._serial += 1
+        self._cur, self._cb = pb, self._cbatch(pb)
+        out = L.MfvaeOutputs()
+        L.check(lib.mfvae_fwd_bwd(self._h, C.byref(self._cb), C.byref(out), self._stream()))
+        self._losses = self._ws_view(out.d_losses, 1, 4, 4)[0]
+        self.philox_step += 1
+        if self.data_parallel:
+            self._allreduce_grads()
+        self.adam_step(lr, betas, eps)
+        return self._losses

@@ -383,7 +383,8 @@ def philox_normal(seed: int, step: int, sample0: int, n_samples: int, width: int
     """eps[B, width] exactly as the CUDA kernels draw it (see ``csrc/philox.cuh``):
     element (global sample s, column j) uses counter (s_lo, s_hi, j//4, step), key (seed_lo, seed_hi);
     the 4 outputs give 4 normals for columns 4*(j//4)..+3 via two Box-Muller pairs
-    (u = (x + 0.5) * 2^-32;  r = sqrt(-2 ln u0);  n0 = r cos(2 pi u1), n1 = r sin(2 pi u1))."""
+    (u = ((x >> 9) + 0.5) * 2^-23, exactly representable in fp32;  r = sqrt(-2 ln u0);
+    n0 = r cos(2 pi u1), n1 = r sin(2 pi u1))."""
     assert width % 4 == 0
     s = (np.arange(n_samples, dtype=np.uint64) + np.uint64(sample0))[:, None]
     q = np.arange(width // 4, dtype=np.uint64)[None, :]
@@ -395,8 +396,8 @@ def philox_normal(seed: int, step: int, sample0: int, n_samples: int, width: int
     key = np.zeros((n_samples, width // 4, 2), dtype=np.uint32)
     key[..., 0] = np.uint32(seed & 0xFFFFFFFF)
     key[..., 1] = np.uint32((seed >> 32) & 0xFFFFFFFF)
-    r = philox4x32_10(ctr, key).astype(np.float64)
-    u = (r + 0.5) * (1.0 / 4294967296.0)
+    r = (philox4x32_10(ctr, key) >> np.uint32(9)).astype(np.float64)
+    u = (r + 0.5) * (1.0 / 8388608.0)
     rad0 = np.sqrt(-2.0 * np.log(u[..., 0])); rad1 = np.sqrt(-2.0 * np.log(u[..., 2]))
     th0 = 2.0 * np.pi * u[..., 1]; th1 = 2.0 * np.pi * u[..., 3]
     out = np.stack([rad0 * np.cos(th0), rad0 * np.sin(th0), rad1 * np.cos(th1), rad1 * np.sin(th1)], axis=-1)

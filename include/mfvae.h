@@ -6,7 +6,7 @@
  *   model.py:8-16      loss_vae_fn            -> mfvae_loss with joint_mse = 1
  *   main.py:92-93 / trainer.py:98-100  zero_grad + loss.backward() -> mfvae_backward
  *   main.py:97   / trainer.py:102-103  torch.optim.Adam.step()     -> mfvae_adam_step
- *   trainer.py:7-45    create_dataset (host numpy) -> mfvae_stage (device gather from packed rows)
+ *   trainer.py:7-45    create_dataset (host numpy) -> device staging kernel inside the forward entry (MfvaeBatch)
  *   src/replay_buffer.py:53-115 (cpprb, C++) / jax_ver/jax_buffer.py:80-140 (flashbax)
  *                                             -> mfvae_ring_* (HBM-resident ring + gather)
  *

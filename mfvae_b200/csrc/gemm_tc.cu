@@ -1,8 +1,495 @@
-// temporary stub
+// gemm_tc.cu — bf16 tensor-core GEMM for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM -> epilogue.
+//
+//   C[g](m,n) = epi( sum_k A[g](m,k) * B[g](n,k) ),  fp32 accumulation in TMEM.
+//
+// One kernel template covers the three contractions of a Linear layer (reference nn.Linear at
+// torch_ver/model.py:50,53,91,94 and its autograd backward):
+//   forward  Y  = X  W^T      A = X  (K-major)   B = W (K-major)        epilogue: +bias [, relu]
+//   dgrad    dX = dY W        A = dY (K-major)   B = W (MN-major)       epilogue: * (X > 0)
+//   wgrad    dW = dY^T X      A = dY (MN-major)  B = X (MN-major)       epilogue: fp32 (+= with split-K)
+// so no operand is ever transposed in HBM: the UMMA shared-memory descriptors take either major.
+//
+// CTA = 6 warps, persistent over a static round-robin tile schedule:
+//   warp 0      TMA producer   (one lane): cp.async.bulk.tensor.3d into a kStages-deep 128B-swizzled ring
+//   warp 1      MMA issuer     (one lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 per instruction;
+//                              tcgen05.commit releases ring slots and publishes finished accumulators
+//   warps 2..5  epilogue       tcgen05.ld 32 lanes x 32 columns -> registers -> bias/relu/mask -> global
+// TMEM holds two accumulator stages (2 x BN fp32 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
 #include "kernels.h"
+
 namespace mfvae {
-struct TcPlan { GemmOp op; };
-int gemm_tc_plan(const GemmOp& op, TcPlan** out) { *out = new TcPlan{op}; return 0; }
-int gemm_tc_run(const TcPlan* p, cudaStream_t s) { MFVAE_FAIL("tcgen05 path not built yet"); }
-void gemm_tc_free(TcPlan* p) { delete p; }
+
+constexpr int BM = 128;
+constexpr int BK = 64;                    // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int kTcThreads = 192;
+constexpr uint32_t kSpinLimit = 1u << 26; // bounded waits: a protocol bug traps instead of hanging the GPU
+
+struct TcParams {
+  int G, M, N, K;
+  int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
+  long long total_work;
+  void* C; long long c_gs, c_ld; int c_dtype;
+  const float* bias; long long bias_gs;
+  int epi;
+  const __nv_bfloat16* aux; long long aux_gs, aux_ld;
+  int accumulate_atomic;                  // split-K: red.global.add.f32
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < kSpinLimit; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) with SWIZZLE_128B = 2.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+// a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+template <int BN> struct TcCfg {
+  static constexpr int kABytes = BM * BK * 2;                  // 16 KB
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+  static constexpr int kTmemCols = 2 * BN;                     // 128 / 256 / 512: a power of two >= 32
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------------
+// epilogue for one 32-column chunk held by one thread (= one output row)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row, int col0, const uint32_t (&v)[32]) {
+  if (row >= p.M) return;
+  const int ncols = min(32, p.N - col0);
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (p.epi == kEpiBias || p.epi == kEpiBiasRelu) {
+    const float* b = p.bias + g * p.bias_gs + col0;
+    if (ncols == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 bb = *reinterpret_cast<const float4*>(b + j);
+        f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols) f[j] += b[j];
+    }
+    if (p.epi == kEpiBiasRelu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+  } else if (p.epi == kEpiReluMask) {
+    const __nv_bfloat16* a = p.aux + g * p.aux_gs + static_cast<long long>(row) * p.aux_ld + col0;
+    if (ncols == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(a + j);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 m = __bfloat1622float2(h[q]);
+          if (!(m.x > 0.f)) f[j + 2 * q] = 0.f;
+          if (!(m.y > 0.f)) f[j + 2 * q + 1] = 0.f;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols && !(__bfloat162float(a[j]) > 0.f)) f[j] = 0.f;
+    }
+  }
+  if (p.c_dtype == kBF16) {
+    __nv_bfloat16* c = static_cast<__nv_bfloat16*>(p.C) + g * p.c_gs + static_cast<long long>(row) * p.c_ld + col0;
+    if (ncols == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 o;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]), h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(c + j) = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols) c[j] = __float2bfloat16_rn(f[j]);
+    }
+  } else {
+    float* c = static_cast<float*>(p.C) + g * p.c_gs + static_cast<long long>(row) * p.c_ld + col0;
+    if (p.accumulate_atomic) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(c + j, f[j]);
+    } else if (ncols == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols) c[j] = f[j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  using Cfg = TcCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;                                   // [kStages][16 KB]
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;          // [kStages][BN*128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;                                    // TMA -> MMA
+  uint64_t* empty = bars + kStages;                         // MMA -> TMA
+  uint64_t* acc_full = bars + 2 * kStages;                  // MMA -> epilogue   [2]
+  uint64_t* acc_empty = bars + 2 * kStages + 2;             // epilogue -> MMA   [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a); prefetch_tmap(&map_b);
+    for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long tiles_per_split = static_cast<long long>(p.m_tiles) * p.n_tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const int nt = static_cast<int>(w % p.n_tiles);
+        const int mt = static_cast<int>((w / p.n_tiles) % p.m_tiles);
+        const long long r = w / tiles_per_split;
+        const int ks = static_cast<int>(r % p.splits);
+        const int g = static_cast<int>(r / p.splits);
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty + stage, phase ^ 1);
+          mbar_expect_tx(full + stage, Cfg::kStageBytes);
+          uint8_t* sa = smem_a + stage * Cfg::kABytes;
+          uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_3d(sa + j * 8192, &map_a, full + stage, mt * BM + j * 64, kb * BK, g);
+          } else {
+            tma_load_3d(sa, &map_a, full + stage, kb * BK, mt * BM, g);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_3d(sb + j * 8192, &map_b, full + stage, nt * BN + j * 64, kb * BK, g);
+          } else {
+            tma_load_3d(sb, &map_b, full + stage, kb * BK, nt * BN, g);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
+      // K-major SW128: 8-row groups 1024 B apart (SBO), K advance 32 B inside the swizzled row.
+      // MN-major SW128: 64-element MN atoms (BK rows x 128 B = 8192 B apart, LBO), 8-k-row groups 1024 B apart (SBO),
+      //                 K advance 16 rows = 2048 B.
+      constexpr uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
+      constexpr uint32_t a_kstep = A_MN ? 2048u : 32u, b_kstep = B_MN ? 2048u : 32u;
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const long long r = w / tiles_per_split;
+        const int ks = static_cast<int>(r % p.splits);
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        mbar_wait(acc_empty + as, aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * Cfg::kABytes);
+          const uint32_t sb = smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024u);
+            const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024u);
+            umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty + stage);              // frees the smem slot once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(acc_full + as);                // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    int as = 0; uint32_t aphase = 0;
+    for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      const int nt = static_cast<int>(w % p.n_tiles);
+      const int mt = static_cast<int>((w / p.n_tiles) % p.m_tiles);
+      const long long r = w / tiles_per_split;
+      const int ks = static_cast<int>(r % p.splits);
+      const int g = static_cast<int>(r / p.splits);
+      const bool has_k = ks * p.kb_per_split < p.k_blocks;
+      mbar_wait(acc_full + as, aphase);
+      tc_fence_after();
+      const int row = mt * BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = nt * BN + c * 32;
+        if (col0 >= p.N) break;
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        if (has_k) epilogue_chunk(p, g, row, col0, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + as);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct TcPlan {
+  GemmOp op;
+  TcParams prm;
+  CUtensorMap map_a, map_b;
+  int BN = 0; bool a_mn = false, b_mn = false;
+  int grid = 0;
+};
+
+// operand(r, k) with element strides (rs, cs): K-major when cs == 1, MN-major when rs == 1
+static int encode_operand(CUtensorMap* map, const void* base, int rows, int K, int G, int64_t gs, int64_t rs, int64_t cs,
+                          int box_rows_kmajor, bool* is_mn) {
+  EncodeTiledFn enc = get_encode_fn();
+  MFVAE_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  MFVAE_CHECK(reinterpret_cast<uintptr_t>(base) % 16 == 0, "tcgen05 GEMM: operand base must be 16-byte aligned");
+  const bool mn = (rs == 1 && cs != 1);
+  *is_mn = mn;
+  MFVAE_CHECK(mn || cs == 1, "tcgen05 GEMM: one operand stride must be 1");
+  const int64_t ld = mn ? cs : rs;
+  MFVAE_CHECK(ld % 8 == 0, "tcgen05 GEMM: leading dimension must be a multiple of 8 elements (16 bytes)");
+  MFVAE_CHECK(G == 1 || (gs % 8 == 0 && gs > 0), "tcgen05 GEMM: group stride must be a positive multiple of 8 elements");
+  cuuint64_t dims[3], strides[2];
+  cuuint32_t box[3], estr[3] = {1, 1, 1};
+  const int inner = mn ? rows : K, outer = mn ? K : rows;
+  dims[0] = static_cast<cuuint64_t>(inner); dims[1] = static_cast<cuuint64_t>(outer); dims[2] = static_cast<cuuint64_t>(G);
+  strides[0] = static_cast<cuuint64_t>(ld) * 2;
+  strides[1] = static_cast<cuuint64_t>(G == 1 ? static_cast<int64_t>(outer) * ld : gs) * 2;
+  box[0] = 64; box[1] = static_cast<cuuint32_t>(mn ? BK : box_rows_kmajor); box[2] = 1;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MFVAE_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc(const TcPlan* pl, cudaStream_t s) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  if (!attr_set) {
+    MFVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  kern<<<pl->grid, kTcThreads, Cfg::kSmemBytes, s>>>(pl->map_a, pl->map_b, pl->prm);
+  MFVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+static int launch_tc_major(const TcPlan* pl, cudaStream_t s) {
+  if (!pl->a_mn && !pl->b_mn) return launch_tc<BN, false, false>(pl, s);
+  if (!pl->a_mn && pl->b_mn) return launch_tc<BN, false, true>(pl, s);
+  if (pl->a_mn && pl->b_mn) return launch_tc<BN, true, true>(pl, s);
+  return launch_tc<BN, true, false>(pl, s);
+}
+
+int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
+  MFVAE_CHECK(op.dtype == kBF16, "tcgen05 GEMM: operands must be bf16");
+  MFVAE_CHECK(op.M > 0 && op.N > 0 && op.K > 0 && op.G > 0, "tcgen05 GEMM: empty problem");
+  MFVAE_CHECK(op.epi != kEpiAccum || op.c_dtype == kF32, "tcgen05 GEMM: accumulate epilogue needs fp32 C");
+  MFVAE_CHECK(op.split_k == 1 || op.epi == kEpiAccum, "tcgen05 GEMM: split-K needs the accumulate epilogue");
+  MFVAE_CHECK(op.c_ld % (op.c_dtype == kBF16 ? 8 : 4) == 0 && op.c_gs % 8 == 0, "tcgen05 GEMM: C leading dimension / group stride alignment");
+  MFVAE_CHECK(reinterpret_cast<uintptr_t>(op.C) % 16 == 0, "tcgen05 GEMM: C must be 16-byte aligned");
+  MFVAE_CHECK(op.epi != kEpiReluMask || (op.aux && op.aux_ld % 8 == 0 && op.aux_gs % 8 == 0 && reinterpret_cast<uintptr_t>(op.aux) % 16 == 0),
+              "tcgen05 GEMM: relu-mask aux alignment");
+  MFVAE_CHECK((op.epi != kEpiBias && op.epi != kEpiBiasRelu) || (op.bias && reinterpret_cast<uintptr_t>(op.bias) % 16 == 0 && op.bias_gs % 4 == 0),
+              "tcgen05 GEMM: bias alignment");
+  TcPlan* pl = new TcPlan();
+  pl->op = op;
+  const int m_tiles = (op.M + BM - 1) / BM;
+  // tile width: the widest BN that still gives every SM a tile; otherwise the narrowest that covers N
+  int BN = 64;
+  {
+    const int cands[3] = {256, 128, 64};
+    for (int c : cands) {
+      if (c > 64 && c / 2 >= op.N) continue;        // do not pad N by 2x or more
+      const long long t = static_cast<long long>(op.G) * m_tiles * ((op.N + c - 1) / c);
+      if (t >= kNumSMs) { BN = c; break; }
+    }
+  }
+  const int n_tiles = (op.N + BN - 1) / BN;
+  const int k_blocks = (op.K + BK - 1) / BK;
+  int splits = 1;
+  if (op.epi == kEpiAccum) {
+    const long long tiles = static_cast<long long>(op.G) * m_tiles * n_tiles;
+    long long want = op.split_k > 1 ? op.split_k : 1;
+    want = std::max<long long>(want, (kNumSMs + tiles - 1) / tiles);
+    splits = static_cast<int>(std::max<long long>(1, std::min<long long>(want, std::max(1, k_blocks / 4))));
+  }
+  const int kb_per_split = (k_blocks + splits - 1) / splits;
+  splits = (k_blocks + kb_per_split - 1) / kb_per_split;       // no empty splits
+  TcParams& p = pl->prm;
+  p.G = op.G; p.M = op.M; p.N = op.N; p.K = op.K;
+  p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.k_blocks = k_blocks; p.splits = splits; p.kb_per_split = kb_per_split;
+  p.total_work = static_cast<long long>(op.G) * splits * m_tiles * n_tiles;
+  p.C = op.C; p.c_gs = op.c_gs; p.c_ld = op.c_ld; p.c_dtype = op.c_dtype;
+  p.bias = op.bias; p.bias_gs = op.bias_gs; p.epi = op.epi;
+  p.aux = static_cast<const __nv_bfloat16*>(op.aux); p.aux_gs = op.aux_gs; p.aux_ld = op.aux_ld;
+  p.accumulate_atomic = (op.epi == kEpiAccum) ? 1 : 0;
+  pl->BN = BN;
+  pl->grid = static_cast<int>(std::min<long long>(p.total_work, kNumSMs));
+  int rc = encode_operand(&pl->map_a, op.A, op.M, op.K, op.G, op.a_gs, op.a_rs, op.a_cs, BM, &pl->a_mn);
+  if (rc == 0) rc = encode_operand(&pl->map_b, op.B, op.N, op.K, op.G, op.b_gs, op.b_rs, op.b_cs, BN, &pl->b_mn);
+  if (rc != 0) { delete pl; return rc; }
+  *out = pl;
+  return 0;
+}
+
+int gemm_tc_run(const TcPlan* pl, cudaStream_t s) {
+  MFVAE_CHECK(pl != nullptr, "tcgen05 GEMM: null plan");
+  switch (pl->BN) {
+    case 64: return launch_tc_major<64>(pl, s);
+    case 128: return launch_tc_major<128>(pl, s);
+    case 256: return launch_tc_major<256>(pl, s);
+  }
+  MFVAE_FAIL("tcgen05 GEMM: unsupported tile width");
+}
+
+void gemm_tc_free(TcPlan* p) { delete p; }
+
+}  // namespace mfvae

@@ -491,6 +491,18 @@ int mfvae_create(const MfvaeConfig* cfg, int device, MfvaeHandle* out) {
   h->n_act.assign(cfg->n_act, cfg->n_act + cfg->n_agents);
   h->cfg.obs_dim = h->obs_dim.data(); h->cfg.n_act = h->n_act.data();
   if (build_layout(h) != 0) { delete h; return 1; }
+  // buckets in backward-completion order
+  auto add_bucket = [&](int64_t b, int64_t e) {
+    MfvaeHandle_::Bucket k{b, e, nullptr};
+    if (device >= 0) cudaEventCreateWithFlags(&k.ev, cudaEventDisableTiming);
+    h->buckets.push_back(k);
+  };
+  const int64_t l1 = (h->cfg.n_dec_hidden > 1) ? h->decW[1].off : h->reg3_begin;
+  add_bucket(h->reg3_begin, h->enc_begin);           // output layers + reward_linear
+  add_bucket(l1, h->reg3_begin);                      // decoder hidden layers >= 1 (may be empty)
+  add_bucket(h->reg2_begin, l1);                      // decoder layer 0 (largest)
+  add_bucket(0, h->reg2_begin);                       // idx_emb
+  if (h->cfg.optimize_encoders) add_bucket(h->enc_begin, h->arena_elems);
   if (device < 0) { *out = h; return 0; }        // layout-only handle
   std::vector<int32_t> meta;
   meta.insert(meta.end(), h->obs_off.begin(), h->obs_off.end());
@@ -500,18 +512,6 @@ int mfvae_create(const MfvaeConfig* cfg, int device, MfvaeHandle* out) {
       cudaMemcpy(h->d_meta, meta.data(), meta.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
     delete h; MFVAE_FAIL("cudaMalloc / cudaMemcpy of the agent table failed");
   }
-  // buckets in backward-completion order
-  auto add_bucket = [&](int64_t b, int64_t e) {
-    MfvaeHandle_::Bucket k{b, e, nullptr};
-    cudaEventCreateWithFlags(&k.ev, cudaEventDisableTiming);
-    h->buckets.push_back(k);
-  };
-  const int64_t l1 = (h->cfg.n_dec_hidden > 1) ? h->decW[1].off : h->reg3_begin;
-  add_bucket(h->reg3_begin, h->enc_begin);           // output layers + reward_linear
-  add_bucket(l1, h->reg3_begin);                      // decoder hidden layers >= 1 (may be empty)
-  add_bucket(h->reg2_begin, l1);                      // decoder layer 0 (largest)
-  add_bucket(0, h->reg2_begin);                       // idx_emb
-  if (h->cfg.optimize_encoders) add_bucket(h->enc_begin, h->arena_elems);
   *out = h;
   return 0;
 }

@@ -1,0 +1,130 @@
+"""Run a golden case through the CUDA path and report its deviation from (a) the golden vectors minted from the
+reference and (b) the oracle, as one JSON line.  Run in its own process (a device trap must not poison pytest):
+
+    python tests/step_check.py <case> <fp32|bf16> <auto|simt|tcgen05> [dropin|fast] [philox]
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import mavae_oracle as O                     # noqa: E402
+from tests.golden_util import load_case, digest, step_inputs   # noqa: E402
+import mfvae_b200 as M                                     # noqa: E402
+
+
+def rel_l2(got, want):
+    got = got.detach().double().cpu(); want = want.detach().double().cpu()
+    return float((got - want).norm() / max(float(want.norm()), 1e-30))
+
+
+def digest_err(got, want):
+    l2 = max(abs(want[1]), 1e-30)
+    scale = max(np.abs(want[2:]).max(), 1e-30)
+    return max(abs(got[1] - want[1]) / l2, float(np.abs(got[2:] - want[2:]).max() / scale))
+
+
+def main(case, precision, engine, mode="dropin", rng="eps"):
+    spec, rec = load_case(case)
+    dev = "cuda:0"
+    huber = bool(rec["huber"])
+    m = M.MAVAE(spec.idx_features, spec.latent, spec.act_features, True, spec.agents, spec.obs_dim, spec.n_act, dev,
+                precision=precision, engine=engine, huber=huber)
+    P = O.init_params(spec, int(rec["param_seed"]))
+    m.load_named(P)
+    st = O.OracleState(spec, {k: v.clone() for k, v in P.items() if not k.startswith("decoder.")})
+    opt = M.FusedAdam(m, 0.005)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=50, eta_min=1e-4)
+    L = spec.latent
+    out = {"case": case, "precision": precision, "engine": engine, "mode": mode, "rng": rng,
+           "loss_rel_golden": [], "loss_rel_oracle": [], "losses": []}
+    for step in range(3):
+        trans, codebook, eps_all = step_inputs(spec, rec, step)
+        idx_state, acts, joint, nxt, rew = M.create_dataset(trans, codebook)
+        m.philox_step = step
+        eps_dev = eps_all.to(dev)
+        if rng == "philox":
+            # draw inside the kernels; the oracle is fed the kernel's own stream (dumped through the C ABI)
+            import ctypes as C
+            from mfvae_b200 import _lib as Lb
+            dump = torch.empty(int(rec["batch"]), spec.n_agents * L, device=dev)
+            Lb.check(Lb.lib().mfvae_philox_normal(Lb.ptr(dump), dump.shape[0], dump.shape[1], m.philox_seed, step, 0,
+                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            torch.cuda.synchronize()
+            out.setdefault("philox_vs_numpy_maxabs", []).append(float((dump.cpu() - eps_all).abs().max()))
+            eps_all = dump.cpu()
+            eps_dev = None
+        lr = opt.param_groups[0]["lr"]
+        if mode == "dropin":
+            recon_s, recon_r, mu_all, lv_all = m(idx_state, acts, eps=eps_dev)
+            loss, sl, rl, kl = M.loss_s_r_vae_fn(recon_s, recon_r, nxt, rew, mu_all, lv_all, dev, using_huber_loss=huber)
+            opt.zero_grad()
+            loss.backward()
+        elif mode == "torchloss":
+            # the reference's own loss arithmetic in torch ops on our outputs -> autograd bridge (backward_ext)
+            recon_s, recon_r, mu_all, lv_all = m(idx_state, acts, eps=eps_dev)
+            F = torch.nn.functional
+            fn = F.huber_loss if huber else F.mse_loss
+            sl = fn(nxt.to(dev), recon_s); rl = fn(rew.to(dev), recon_r)
+            kl = 0.0
+            for mu_, lv_ in zip(mu_all, lv_all):
+                kl = kl + torch.mean(-0.5 * torch.sum(1 + lv_ - mu_ ** 2 - torch.exp(lv_), 1), 0)
+            loss = sl + 0.005 * rl + 0.0025 * kl
+            loss.backward()
+        else:
+            pb = m.pack(idx_state, acts, eps=eps_dev)
+            pb.next, pb.rew = nxt.to(dev), rew.to(dev)
+            pb.idx = None
+        eps = {a: eps_all[:, i * L:(i + 1) * L] for i, a in enumerate(spec.agents)}
+        if mode == "fast":
+            # fast path = fwd+loss+bwd+adam in one call; compare losses and the post-step parameters only
+            losses_dev = m.train_step(pb, lr)
+            sched.step()
+            got_losses = [float(x) for x in losses_dev.cpu()]
+            o_losses, G, outs = O.train_step(st, idx_state, acts, eps, nxt, rew, lr, huber)
+        else:
+            got_losses = [float(loss), float(sl), float(rl), float(kl)]
+            # oracle on the same inputs, same current parameters
+            o_losses, G, outs = O.grads(st.P, spec, idx_state, acts, eps, nxt, rew, huber)
+            if step == 0:
+                rs, rr, mus, lvs = outs
+                out["recon_s_rel"] = rel_l2(recon_s, rs); out["recon_r_rel"] = rel_l2(recon_r, rr)
+                out["mu_rel"] = rel_l2(torch.cat(list(mu_all), 1), torch.cat(mus, 1))
+                out["logvar_rel"] = rel_l2(torch.cat(list(lv_all), 1), torch.cat(lvs, 1))
+                out["golden_out_err"] = max(
+                    digest_err(digest(recon_s, "out.recon_s"), rec["out.recon_s"]),
+                    digest_err(digest(recon_r, "out.recon_r"), rec["out.recon_r"]),
+                    digest_err(digest(torch.cat(list(mu_all), 1), "out.mu"), rec["out.mu"]),
+                    digest_err(digest(torch.cat(list(lv_all), 1), "out.logvar"), rec["out.logvar"]))
+                mine = m.named_arena_tensors()
+                gerr, gold = {}, {}
+                for k, p in mine.items():
+                    gerr[k] = rel_l2(p.grad, G[k])
+                    gold[k] = digest_err(digest(p.grad, "grad." + k), rec["grad." + k])
+                worst = max(gerr, key=gerr.get)
+                out["grad_rel_max"] = gerr[worst]; out["grad_rel_worst"] = worst
+                out["grad_rel_median"] = float(np.median(list(gerr.values())))
+                big = {k: v for k, v in gerr.items() if k.startswith(("state_decoder", "reward_decoder", "idx_emb", "reward_linear"))}
+                out["grad_rel_max_registered"] = max(big.values())
+                gw = max(gold, key=gold.get)
+                out["golden_grad_err"] = gold[gw]; out["golden_grad_worst"] = gw
+            opt.step()
+            sched.step()
+            O.train_step(st, idx_state, acts, eps, nxt, rew, lr, huber)
+        out["losses"].append(got_losses)
+        out["loss_rel_golden"].append(max(abs(g - w) / max(abs(w), 1e-30) for g, w in zip(got_losses, rec["losses"][step])))
+        out["loss_rel_oracle"].append(max(abs(g - w) / max(abs(w), 1e-30) for g, w in zip(got_losses, o_losses)))
+    torch.cuda.synchronize()
+    mine = m.named_arena_tensors()
+    perr = {k: rel_l2(p, st.P[k]) for k, p in mine.items()}
+    pw = max(perr, key=perr.get)
+    out["param3_rel_max"] = perr[pw]; out["param3_worst"] = pw
+    out["golden_param3_err"] = max(digest_err(digest(p, "param3." + k), rec["param3." + k]) for k, p in mine.items())
+    print("STEP_CHECK " + json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main(*sys.argv[1:])

@@ -1,0 +1,144 @@
+"""CPU: the C-ABI library loads and exports every symbol include/mfvae.h declares; host-side logic
+(arena table, parameter views, state_dict surface, staging) behaves like the reference's."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mavae_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    from mfvae_b200 import build
+    build.build()
+    import mfvae_b200
+    return mfvae_b200
+
+
+def test_every_declared_symbol_is_exported(built):
+    hdr = open(os.path.join(ROOT, "include", "mfvae.h")).read()
+    declared = set(re.findall(r"\b(mfvae_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = C.CDLL(built._lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(built._lib.SIGNATURES), declared ^ set(built._lib.SIGNATURES)
+    assert built._lib.lib().mfvae_version() >= 100
+
+
+def test_no_cpu_path(built):
+    spec = O.tiny_spec(3, idx_features=16, latent=8, act_features=8)
+    m = built.MAVAE(16, 8, 8, True, spec.agents, spec.obs_dim, spec.n_act, "cpu", precision="fp32")
+    t = O.synth_transition(spec, 4, 0)
+    idx_state, acts, *_ = built.create_dataset(t, {a: i for i, a in enumerate(spec.agents)})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(idx_state, acts)
+    with pytest.raises(RuntimeError):
+        m.adam_step(1e-3)
+
+
+def test_state_dict_surface_matches_reference(built):
+    """39 keys with the reference's names and the reference's registered parameter count."""
+    spec = O.simple_tag_spec()
+    m = built.MAVAE(64, 64, 64, True, spec.agents, spec.obs_dim, spec.n_act, "cpu")
+    keys = list(m.state_dict().keys())
+    want = ["idx_emb.weight"]
+    for pre in ("decoder", "state_decoder", "reward_decoder"):
+        for i in (0, 2, 4, 6, 8, 10):
+            want += [f"{pre}.net.{i}.weight", f"{pre}.net.{i}.bias"]
+    want += ["reward_linear.weight", "reward_linear.bias"]
+    assert keys == want
+    assert sum(p.numel() for p in m.parameters()) == 29_096_880           # SURVEY appendix A [probe]
+    live = sum(p.numel() for n, p in m.named_parameters() if not n.startswith("decoder."))
+    assert live == 17_451_820
+    assert isinstance(m.encoders, dict) and not isinstance(m.encoders, torch.nn.ModuleDict)
+    assert sum(p.numel() for e in m.encoders.values() for p in e.parameters()) == 2_676_480
+    assert m.reward_linear.weight.shape == (40, 40) and bool((m.reward_linear.weight == 1).all())
+    assert m.state_decoder.net[10].weight.shape == (5660, 1024)
+    assert m.encoders["adversary_0"].net[0].weight.shape == (64, 206)
+    assert m.encoders["agent_0"].net[0].weight.shape == (64, 204)
+    # parameters are views of one arena and share its version counter
+    v0 = m._arena._version
+    with torch.no_grad():
+        m.state_decoder.net[0].bias.add_(1.0)
+    assert m._arena._version > v0
+    sd = m.state_dict()
+    m2 = built.MAVAE(64, 64, 64, True, spec.agents, spec.obs_dim, spec.n_act, "cpu")
+    m2.load_state_dict(sd)
+    assert torch.equal(m2.state_decoder.net[0].bias, m.state_decoder.net[0].bias)
+
+
+def test_load_named_roundtrip(built):
+    spec = O.tiny_spec(3, idx_features=16, latent=8, act_features=8)
+    P = O.init_params(spec, 3)
+    m = built.MAVAE(16, 8, 8, True, spec.agents, spec.obs_dim, spec.n_act, "cpu", precision="fp32")
+    m.load_named(P)
+    mine = m.named_arena_tensors()
+    assert set(mine) == set(P)
+    for k in P:
+        assert torch.equal(mine[k], P[k]), k
+    # padding columns of the first encoder layer stay zero
+    for t in m._table:
+        if t.cols != t.ld:
+            blk = m._arena[t.offset:t.offset + t.rows * t.ld].view(t.rows, t.ld)
+            assert float(blk[:, t.cols:].abs().max()) == 0.0
+
+
+def test_create_dataset_matches_reference_restatement(built):
+    spec = O.tiny_spec(4)
+    t = O.synth_transition(spec, 9, seed=11)
+    cb = {a: i for i, a in enumerate(spec.agents)}
+    got = built.create_dataset(t, cb)
+    want = O.stage_batch(t, cb)
+    for a in spec.agents:
+        assert torch.equal(got[0][a], want[0][a]) and torch.equal(got[1][a], want[1][a])
+    for g, w in zip(got[2:], want[2:]):
+        assert torch.equal(g, w)
+
+
+def test_host_stager_cpu(built):
+    spec = O.tiny_spec(3)
+    t = O.synth_transition(spec, 6, seed=5)
+    cb = {a: i for i, a in enumerate(spec.agents)}
+    pb = built.HostStager("cpu").stage(t, cb)
+    _, _, _, nxt, rew = O.stage_batch(t, cb)
+    assert torch.equal(pb.next, nxt) and torch.equal(pb.rew, rew)
+    assert pb.obs.shape == (6, spec.state_dim) and pb.act.shape == (6, 3)
+
+
+def test_trainer_surface(built):
+    spec = O.tiny_spec(3, idx_features=16, latent=8, act_features=8)
+    m = built.MAVAE(16, 8, 8, True, spec.agents, spec.obs_dim, spec.n_act, "cpu", precision="fp32")
+    with pytest.raises(AssertionError):
+        built.Trainer("SGD", m, 1e-3, built.loss_s_r_vae_fn, device="cpu")
+    tr = built.Trainer("Adam", m, 5e-3, built.loss_s_r_vae_fn, device="cpu")
+    for f in ("sigma", "mu", "nu", "sigma_new", "mu_new", "beta", "lr", "loss_func", "loss", "opt", "device"):
+        assert hasattr(tr, f)
+    y = torch.randn(5, 3)
+    assert torch.equal(tr.normalize(y), y) and torch.equal(tr.denormalize(y), y)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(tr.opt, T_max=50, eta_min=1e-4)   # main.py:53 works on FusedAdam
+    assert abs(tr.opt.param_groups[0]["lr"] - 5e-3) < 1e-12
+    for s in range(1, 4):
+        assert abs(built.cosine_lr(s) - O.cosine_lr(s)) < 1e-15
+    # POP-ART with per-agent statistics keeps the un-normalised output of reward_linear unchanged
+    tr2 = built.Trainer("POPART", m, 5e-3, built.loss_s_r_vae_fn, beta=0.3, device="cpu")
+    x = torch.randn(7, 3)
+    before = tr2.denormalize(torch.nn.functional.linear(x, m.reward_linear.weight, m.reward_linear.bias))
+    tr2.art(torch.randn(64, 3) * 3 + 1); tr2.pop(); tr2.update_stats()
+    after = tr2.denormalize(torch.nn.functional.linear(x, m.reward_linear.weight, m.reward_linear.bias))
+    assert torch.allclose(before, after, atol=1e-5)
+
+
+def test_gradient_buckets_cover_optimized_prefix(built):
+    spec = O.simple_tag_spec()
+    m = built.MAVAE(64, 64, 64, True, spec.agents, spec.obs_dim, spec.n_act, "cpu")
+    b = sorted((lo, hi) for _, lo, hi in m.grad_buckets())
+    assert b[0][0] == 0 and b[-1][1] == m._n_opt
+    for (l0, h0), (l1, h1) in zip(b, b[1:]):
+        assert h0 == l1

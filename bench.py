@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — VAE train samples/sec (ELBO fwd + bwd + Adam step) on N B200s, next to the host-CPU reference arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|ref_dims|wide]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of synthetic transitions: device staging + encoder/decoder
+forward + reparameterisation + ELBO + backward + (N > 1: gradient all-reduce) + Adam.  Weak scaling: the per-GPU
+batch is fixed, `value` is the whole-job samples/s (N * B * K / max-over-ranks device time).
+
+JSON line keys follow the driver contract (metric, value, unit, n_gpus, steps, warmup, ms_per_step, ..., e2e,
+gpu_launches, clocks) plus `roofline` (all tcgen05 GEMM launches of the step, timed live with CUDA events on the
+launching stream) and `cpu_baseline` (the oracle port of the reference step on this box's host cores).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+
+METRIC = "VAE train samples/sec (ELBO fwd+bwd+step)"
+UNIT = "samples/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: "MF-VAE MLP encoder/decoder, batch 4096, latent 32, bf16 on 1 B200"
+    "cfg2": dict(latent=32, batch=4096, enc_hidden=(64, 64, 256), dec_hidden=(1024, 256, 64, 256, 1024), precision="bf16",
+                 name="cfg2: MF-VAE (simple_tag dims: 40 agents, obs 142/140, 5 actions) batch 4096/GPU, latent 32, bf16"),
+    # reference dims (latent 64) at the same batch
+    "ref_dims": dict(latent=64, batch=4096, enc_hidden=(64, 64, 256), dec_hidden=(1024, 256, 64, 256, 1024), precision="bf16",
+                     name="reference dims (latent 64) batch 4096/GPU, bf16"),
+    # BASELINE.json configs[0]: torch_ver/main.py default (B = 128, fp32)
+    "cfg1": dict(latent=64, batch=128, enc_hidden=(64, 64, 256), dec_hidden=(1024, 256, 64, 256, 1024), precision="fp32",
+                 name="cfg1: torch_ver/main.py default, batch 128, fp32"),
+    # BASELINE.json configs[2]: wide MF-VAE
+    "wide": dict(latent=128, batch=4096, enc_hidden=(1024, 1024, 1024, 1024), dec_hidden=(1024, 1024, 1024, 1024),
+                 precision="bf16", name="cfg3: wide (hidden 1024 x4, latent 128) batch 4096/GPU, bf16"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_spec(w):
+    from oracle import mavae_oracle as O
+    return O.simple_tag_spec(latent=w["latent"], enc_hidden=tuple(w["enc_hidden"]), dec_hidden=tuple(w["dec_hidden"]))
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the oracle port of the reference's CPU step (the Python reference cannot travel to the GPU box)
+# ------------------------------------------------------------------------------------------------
+def cpu_step_factory(w, batch):
+    from oracle import mavae_oracle as O
+    spec = make_spec(w)
+    st = O.OracleState(spec, O.init_params(spec, 0))
+    codebook = {a: i for i, a in enumerate(spec.agents)}
+    trans = O.synth_transition(spec, batch, seed=0)
+    eps_all = torch.randn(batch, spec.n_agents * spec.latent)
+    L = spec.latent
+    counter = [0]
+
+    def step():
+        # same work the reference does per step (main.py:84-98): staging, forward, loss, backward, Adam
+        idx_state, acts, joint, nxt, rew = O.stage_batch(trans, codebook)
+        eps = {a: eps_all[:, i * L:(i + 1) * L] for i, a in enumerate(spec.agents)}
+        losses, _, _ = O.train_step(st, idx_state, acts, eps, nxt, rew, O.cosine_lr(counter[0]))
+        counter[0] += 1
+        return losses
+    return step
+
+
+def time_cpu(w, batch, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_step_factory(w, batch)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample of the workload: same model / batch, K steps sized to finish within minutes
+    batch = w["batch"]
+    steps = max(1, min(args.steps, 10))
+    warm = max(1, min(args.warmup, 2))
+    sps, ms = time_cpu(w, batch, steps, warm)
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": w["name"], "batch": batch},
+            "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{steps} full train steps of batch {batch} (oracle port of torch_ver step incl. create_dataset), torch CPU fp32"},
+            "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def synth_device_batches(spec, B, n, device, seed):
+    import mfvae_b200 as M
+    g = torch.Generator(device=device).manual_seed(seed)
+    S, A = spec.state_dim, spec.n_agents
+    out = []
+    for _ in range(n):
+        obs = torch.randn(B, S, device=device, generator=g)
+        nxt = torch.randn(B, S, device=device, generator=g)
+        act = torch.randint(0, 5, (B, A), device=device, generator=g).float()
+        rew = torch.randn(B, A, device=device, generator=g)
+        out.append(M.PackedBatch(obs, act, nxt, rew))
+    return out
+
+
+def flops_per_sample(spec):
+    from oracle import mavae_oracle as O
+    macs = 0
+    for pre, lst in O.layer_dims(spec).items():
+        if pre == "decoder":
+            continue
+        macs += sum(o * i for o, i in lst)
+    macs += spec.n_agents ** 2
+    return 6 * macs
+
+
+def run_ours(args, w):
+    import torch.distributed as dist
+    import mfvae_b200 as M
+    from mfvae_b200 import _lib as L
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl ours) needs a CUDA device: there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    spec = make_spec(w)
+    B = args.batch or w["batch"]
+    m = M.MAVAE(spec.idx_features, spec.latent, spec.act_features, True, spec.agents, spec.obs_dim, spec.n_act, dev,
+                precision=w["precision"], enc_hidden=w["enc_hidden"], dec_hidden=w["dec_hidden"], include_dead_decoder=False)
+    torch.manual_seed(0)
+    m.reset_parameters()
+    if world > 1:
+        m.enable_data_parallel()
+    nb = 4
+    batches = synth_device_batches(spec, B, nb, dev, seed=1234 + rank)
+    for i, pb in enumerate(batches):
+        pb.sample0 = rank * B
+        pb.batch_global = world * B
+    lr = M.cosine_lr
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (`value`) ----
+    for i in range(args.warmup):
+        m.train_step(batches[i % nb], lr(i))
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.lib().mfvae_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        losses = m.train_step(batches[i % nb], lr(args.warmup + i))
+    e1.record()
+    barrier()
+    launches = L.lib().mfvae_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    value = world * B * args.steps / (ms_total * 1e-3)
+    loss_host = [float(x) for x in losses.cpu()]
+
+    # ---- end to end: packed pinned host batch -> H2D -> step -> D2H loss, every step ----
+    S, A = spec.state_dim, spec.n_agents
+    row = 2 * S + 2 * A
+    n_host = 3
+    host = [torch.randn(B * row).pin_memory() for _ in range(n_host)]
+    for hbuf in host:     # valid action codes
+        hbuf[B * S:B * (S + A)] = torch.randint(0, 5, (B * A,)).float()
+    dbuf = [torch.empty(B * row, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    from mfvae_b200.trainer import _split_flat
+    e2e_steps = max(3, min(args.steps, 20))
+    loss_pinned = torch.empty(4).pin_memory()
+
+    def e2e_loop(n):
+        main = torch.cuda.current_stream()
+        for k in range(2):
+            freed[k].record(main)
+        # prologue: copy of step 0
+        with torch.cuda.stream(copy_stream):
+            dbuf[0].copy_(host[0], non_blocking=True); ready[0].record(copy_stream)
+        for i in range(n):
+            k = i % 2
+            if i + 1 < n:     # overlap the next batch's H2D with this step's compute
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[(i + 1) % 2])
+                    dbuf[(i + 1) % 2].copy_(host[(i + 1) % n_host], non_blocking=True); ready[(i + 1) % 2].record(copy_stream)
+            main.wait_event(ready[k])
+            obs, act, nxt, rew = _split_flat(dbuf[k], B, S, A)
+            pb = M.PackedBatch(obs, act, nxt, rew, sample0=rank * B, batch_global=world * B)
+            out = m.train_step(pb, lr(i))
+            freed[k].record(main)
+            loss_pinned.copy_(out, non_blocking=True)
+        main.synchronize()
+
+    e2e_loop(3)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    t0.record()
+    e2e_loop(e2e_steps)
+    t1.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    ms2 = torch.tensor([max(t0.elapsed_time(t1), 0.0)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / (float(ms2) * 1e-3)
+
+    # ---- roofline of the tensor-core GEMMs, timed live with CUDA events on the launching stream ----
+    roof = None
+    pk = peaks()
+    if rank == 0:
+        L.check(L.lib().mfvae_profile_enable(m._h, 1))
+        tim = (L.MfvaeGemmTiming * 256)()
+        acc = {}
+        reps = max(3, min(args.steps, 10))
+        for i in range(reps):
+            m.train_step(batches[i % nb], lr(i))
+            n = L.lib().mfvae_profile_read(m._h, tim, 256)
+            for j in range(n):
+                t = tim[j]
+                key = (t.kind, t.groups, t.M, t.N, t.K, j)
+                acc.setdefault(key, []).append(t.ms)
+        L.check(L.lib().mfvae_profile_enable(m._h, 0))
+        tot_ms, tot_fl, rows = 0.0, 0.0, []
+        for (kind, G, Mm, Nn, Kk, j), v in acc.items():
+            msj = float(np.mean(v)); fl = 2.0 * G * Mm * Nn * Kk
+            tot_ms += msj; tot_fl += fl
+            rows.append({"kind": ["fwd", "dgrad", "wgrad"][kind], "G": G, "M": Mm, "N": Nn, "K": Kk, "ms": round(msj, 4),
+                         "tflops": round(fl / (msj * 1e-3) / 1e12, 1) if msj > 0 else None})
+        rows.sort(key=lambda r: -r["ms"])
+        if tot_ms > 0:
+            ach = tot_fl / (tot_ms * 1e-3) / 1e12
+            bound = "tensor" if w["precision"] == "bf16" else "fp32-simt"
+            roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                    "traffic": None, "kernel": "gemm_tc_kernel (all %d GEMM launches of one step)" % len(rows),
+                    "gemm_ms_per_step": tot_ms, "gemm_flop_per_step": tot_fl, "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
+                    "engine": bound, "top": rows[:8]}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on this box's host cores, bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cb = min(B, 4096)
+        sps, msc = time_cpu(w, cb, 3, 1)
+        cpu = {"value": sps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"3 train steps (+1 warm-up) of batch {cb}, same model, oracle port of the reference step incl. create_dataset, torch CPU fp32",
+               "ms_per_step": msc}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": w["precision"], "data": "synthetic",
+                "config": {"workload": w["name"], "batch_per_gpu": B, "global_batch": world * B,
+                           "parallelism": f"dp{world}", "l2": f"inputs {B * row * 4 / 1e6:.0f} MB/step, {nb} rotating device batches (> 126 MB L2)",
+                           "flop_per_sample": flops_per_sample(spec)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * row * 4, "d2h_bytes_per_step": 16,
+                        "steps": e2e_steps, "wall_s": wall, "api": "MAVAE.train_step(PackedBatch) fed from packed pinned host rows"},
+                "gpu_launches": int(launches), "clocks": clocks, "losses_last_step": loss_host,
+                "model_tflops": value * flops_per_sample(spec) / 1e12 / world,
+                "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.gpus > 1 and world == 1:
+            # convenience: re-launch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -139,6 +139,15 @@ int mfvae_adam_step(MfvaeHandle h, float lr, float beta1, float beta2, float eps
 /* forward + loss + backward in one call (no optimizer; the host all-reduces gradients in between) */
 int mfvae_fwd_bwd(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* stream);
 
+/* instrumentation: number of kernels this library has launched so far (process-wide), and optional CUDA-event
+ * timing of every GEMM launch of the step on its launching stream.  With profiling on, each step records
+ * start/stop events around its GEMM launches; mfvae_profile_read synchronises and returns, per GEMM of the last
+ * step, {M, N, K, groups, kind (0 fwd, 1 dgrad, 2 wgrad), milliseconds}. */
+uint64_t mfvae_launch_count(void);
+typedef struct MfvaeGemmTiming { int32_t M, N, K, groups, kind; float ms; } MfvaeGemmTiming;
+int mfvae_profile_enable(MfvaeHandle h, int32_t on);
+int32_t mfvae_profile_read(MfvaeHandle h, MfvaeGemmTiming* out, int32_t capacity);
+
 /* gradient buckets in backward-completion order, for the overlapped all-reduce: bucket i covers
  * arena elements [begin, end) and is final once event i (cudaEvent_t, returned as void*) fires. */
 int32_t mfvae_bucket_count(MfvaeHandle h);

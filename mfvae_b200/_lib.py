@@ -41,6 +41,11 @@ class MfvaeBatch(C.Structure):
                 ("batch_global", C.c_int64), ("seed", C.c_uint64), ("step", C.c_uint64)]
 
 
+class MfvaeGemmTiming(C.Structure):
+    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("groups", C.c_int32), ("kind", C.c_int32),
+                ("ms", C.c_float)]
+
+
 class MfvaeOutputs(C.Structure):
     _fields_ = [("d_recon_s", C.c_void_p), ("recon_s_ld", C.c_int32), ("d_recon_r", C.c_void_p),
                 ("recon_r_ld", C.c_int32), ("d_latent", C.c_void_p), ("d_losses", C.c_void_p)]
@@ -68,6 +73,9 @@ SIGNATURES = {
     "mfvae_backward_ext": (C.c_int, [_vp, C.POINTER(MfvaeBatch), _vp, _i64, _vp, _i64, _vp, _vp]),
     "mfvae_adam_step": (C.c_int, [_vp, _f, _f, _f, _f, _i64, _vp]),
     "mfvae_fwd_bwd": (C.c_int, [_vp, C.POINTER(MfvaeBatch), C.POINTER(MfvaeOutputs), _vp]),
+    "mfvae_launch_count": (C.c_uint64, []),
+    "mfvae_profile_enable": (C.c_int, [_vp, _i32]),
+    "mfvae_profile_read": (_i32, [_vp, C.POINTER(MfvaeGemmTiming), _i32]),
     "mfvae_bucket_count": (_i32, [_vp]),
     "mfvae_bucket": (C.c_int, [_vp, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_vp)]),
     "mfvae_bucket_wait": (C.c_int, [_vp, _i32, _vp]),

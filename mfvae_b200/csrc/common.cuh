@@ -21,7 +21,8 @@ int fail(const char* file, int line, const std::string& msg);
 #define MFVAE_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) \
     MFVAE_FAIL(std::string(#expr) + ": " + cudaGetErrorString(e__)); } while (0)
 #define MFVAE_TRY(expr) do { int r__ = (expr); if (r__ != 0) return r__; } while (0)
-#define MFVAE_LAUNCH_CHECK() MFVAE_CUDA(cudaGetLastError())
+extern unsigned long long g_launch_count;      // kernels launched by this library (bench.py's gpu_launches)
+#define MFVAE_LAUNCH_CHECK() do { ++::mfvae::g_launch_count; MFVAE_CUDA(cudaGetLastError()); } while (0)
 
 constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs
 

@@ -114,6 +114,7 @@ int launch_stage(const StageArgs& a, cudaStream_t s) {
     stage_kernel<float><<<grid_for(t0), kThreads, 0, s>>>(a);
     act_embed_kernel<float><<<grid_for(t1), kThreads, 0, s>>>(a);
   }
+  ++g_launch_count;
   MFVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -19,6 +19,7 @@
 
 namespace mfvae {
 
+unsigned long long g_launch_count = 0;
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(const char* file, int line, const std::string& msg) {
@@ -68,6 +69,11 @@ struct MfvaeHandle_ {
   std::vector<int> g_enc_fwd, g_enc_wg, g_enc_dg, g_dec_fwd, g_dec_wg, g_dec_dg;
   int g_sout_fwd = -1, g_rout_fwd = -1, g_rl_fwd = -1;
   int g_sout_wg = -1, g_sout_dg = -1, g_rout_wg = -1, g_rout_dg = -1, g_rl_wg = -1, g_rl_dg = -1;
+
+  // optional per-GEMM event timing (bench.py roofline)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_ev;          // 2 per GEMM op
+  std::vector<char> prof_hit;
 
   // gradient buckets (arena ranges) and their completion events
   struct Bucket { int64_t begin, end; cudaEvent_t ev; };
@@ -329,8 +335,11 @@ static int build_ops(MfvaeHandle_* h) {
 }
 
 static int run_gemm(MfvaeHandle_* h, int i, cudaStream_t s) {
-  if (h->use_tc) return gemm_tc_run(h->tc[i], s);
-  return gemm_simt(h->gemms[i], s);
+  const bool prof = h->profiling && static_cast<size_t>(2 * i + 1) < h->prof_ev.size();
+  if (prof) MFVAE_CUDA(cudaEventRecord(h->prof_ev[2 * i], s));
+  int rc = h->use_tc ? gemm_tc_run(h->tc[i], s) : gemm_simt(h->gemms[i], s);
+  if (prof && rc == 0) { MFVAE_CUDA(cudaEventRecord(h->prof_ev[2 * i + 1], s)); h->prof_hit[i] = 1; }
+  return rc;
 }
 
 static int check_ready(MfvaeHandle_* h, const MfvaeBatch* b) {
@@ -520,6 +529,7 @@ int mfvae_destroy(MfvaeHandle h) {
   if (!h) return 0;
   free_plans(h);
   for (auto& b : h->buckets) if (b.ev) cudaEventDestroy(b.ev);
+  for (auto e : h->prof_ev) cudaEventDestroy(e);
   if (h->d_meta) cudaFree(h->d_meta);
   delete h;
   return 0;
@@ -616,6 +626,35 @@ int mfvae_adam_step(MfvaeHandle h, float lr, float beta1, float beta2, float eps
   return launch_adam(h->ar.d_param, h->ar.d_grad, h->ar.d_m, h->ar.d_v,
                      static_cast<__nv_bfloat16*>(h->ar.d_shadow_bf16), h->optimized_elems, lr, beta1, beta2, eps, t,
                      static_cast<cudaStream_t>(stream));
+}
+
+uint64_t mfvae_launch_count(void) { return g_launch_count; }
+
+int mfvae_profile_enable(MfvaeHandle h, int32_t on) {
+  MFVAE_CHECK(h, "null handle");
+  if (on) {
+    while (h->prof_ev.size() < 2 * h->gemms.size()) {
+      cudaEvent_t e; MFVAE_CUDA(cudaEventCreate(&e)); h->prof_ev.push_back(e);
+    }
+    h->prof_hit.assign(h->gemms.size(), 0);
+  }
+  h->profiling = on != 0;
+  return 0;
+}
+
+int32_t mfvae_profile_read(MfvaeHandle h, MfvaeGemmTiming* out, int32_t capacity) {
+  if (!h || !out) return -1;
+  int32_t n = 0;
+  for (size_t i = 0; i < h->gemms.size() && i < h->prof_hit.size() && n < capacity; ++i) {
+    if (!h->prof_hit[i]) continue;
+    if (cudaEventSynchronize(h->prof_ev[2 * i + 1]) != cudaSuccess) return -1;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]) != cudaSuccess) return -1;
+    const GemmOp& o = h->gemms[i];
+    const int kind = (o.epi == kEpiAccum) ? 2 : ((o.b_rs == 1 && o.b_cs != 1) ? 1 : 0);
+    out[n++] = MfvaeGemmTiming{o.M, o.N, o.K, o.G, kind, ms};
+  }
+  return n;
 }
 
 int32_t mfvae_bucket_count(MfvaeHandle h) { return h ? static_cast<int32_t>(h->buckets.size()) : -1; }

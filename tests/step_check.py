@@ -104,6 +104,7 @@ def main(case, precision, engine, mode="dropin", rng="eps"):
                 for k, p in mine.items():
                     gerr[k] = rel_l2(p.grad, G[k])
                     gold[k] = digest_err(digest(p.grad, "grad." + k), rec["grad." + k])
+                out["grad_rel_top"] = sorted(((round(v, 6), k) for k, v in gerr.items()), reverse=True)[:10]
                 worst = max(gerr, key=gerr.get)
                 out["grad_rel_max"] = gerr[worst]; out["grad_rel_worst"] = worst
                 out["grad_rel_median"] = float(np.median(list(gerr.values())))

@@ -80,3 +80,14 @@ def test_philox_normal_moments():
     # counter-based: a shard starting at sample 1024 equals the slice of the global draw
     s = O.philox_normal(0x5EED, 3, 1024, 128, 64)
     assert np.array_equal(s, e[1024:1152])
+
+
+def test_explicit_huber_formula_equals_library():
+    g = torch.Generator().manual_seed(0)
+    x = 3 * torch.randn(64, 37, generator=g, dtype=torch.float64); y = torch.randn(64, 37, generator=g, dtype=torch.float64)
+    assert abs(float(O.huber_mean(x, y)) - float(torch.nn.functional.huber_loss(x, y))) < 1e-12
+    v, gr = O.np_recon_loss(x.numpy(), y.numpy(), True, 0.5, x.numel())
+    xr = x.clone().requires_grad_(True)
+    (0.5 * torch.nn.functional.huber_loss(xr, y)).backward()
+    assert abs(v - float(torch.nn.functional.huber_loss(x, y))) < 1e-12
+    assert float((xr.grad - torch.from_numpy(gr)).abs().max()) < 1e-15

@@ -539,12 +539,22 @@ class MAVAE(nn.Module):
         return out
 
     def _allreduce_grads(self):
+        """SUM all-reduce of the gradient buckets (the loss-gradient kernels already divide by the GLOBAL batch, so
+        no averaging pass is needed) and of the 4 partial loss scalars.  On the GPU each bucket is reduced on the
+        side stream as soon as its completion event fires, overlapping the rest of backward."""
         import torch.distributed as dist
+        buckets = self.grad_buckets()
+        if not self._on_gpu:           # host-logic path exercised by the gloo tests; no compute happens on CPU
+            for _, b, e in buckets:
+                dist.all_reduce(self._grad[b:e], group=self._pg)
+            if getattr(self, "_losses", None) is not None:
+                dist.all_reduce(self._losses, group=self._pg)
+            return
         lib = L.lib()
         works = []
         main = torch.cuda.current_stream(self._tdev)
         with torch.cuda.stream(self._comm_stream):
-            for i, b, e in self.grad_buckets():
+            for i, b, e in buckets:
                 L.check(lib.mfvae_bucket_wait(self._h, i, C.c_void_p(self._comm_stream.cuda_stream)))
                 works.append(dist.all_reduce(self._grad[b:e], group=self._pg, async_op=True))
             self._comm_stream.wait_stream(main)       # losses are final at the end of the main stream's queue

@@ -187,19 +187,41 @@ def stage_batch(transition: Dict[str, np.ndarray], codebook: Dict[str, int]):
 # ----------------------------------------------------------------------------------------------
 # forward / loss
 # ----------------------------------------------------------------------------------------------
-def _mlp(P, prefix: str, n_layers: int, x: torch.Tensor) -> torch.Tensor:
+class _RoundBF16(torch.autograd.Function):
+    """Round-to-nearest-even to bfloat16 in the forward and / or the backward direction.  Used only by the
+    ``emulate_bf16`` mode, which evaluates the reference algorithm with the operand rounding points of the bf16 CUDA
+    path (GEMM operands and stored activations / activation gradients in bf16, fp32 accumulation, fp32 biases,
+    losses and master weights) so that the tensor-core kernels can be checked to ~1e-3 instead of against an fp32
+    run whose ReLU masks differ in a fraction of units."""
+
+    @staticmethod
+    def forward(ctx, x, fwd, bwd):
+        ctx.bwd = bwd
+        return x.to(torch.bfloat16).to(x.dtype) if fwd else x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.to(torch.bfloat16).to(g.dtype) if ctx.bwd else g), None, None
+
+
+def _q(x, on, fwd=True, bwd=True):
+    return _RoundBF16.apply(x, fwd, bwd) if on else x
+
+
+def _mlp(P, prefix: str, n_layers: int, x: torch.Tensor, q: bool = False, out_fwd: bool = False) -> torch.Tensor:
     names = _linear_names(prefix, n_layers)
     for i, (wn, bn) in enumerate(names):
-        x = torch.nn.functional.linear(x, P[wn], P[bn])      # nn.Linear: x W^T + b
+        x = torch.nn.functional.linear(x, _q(P[wn], q, True, False), P[bn])      # nn.Linear: x W^T + b
         if i + 1 < n_layers:
-            x = torch.relu(x)
-    return x
+            x = _q(torch.relu(x), q)
+    return _q(x, q, out_fwd, True)
 
 
 def forward(P: Dict[str, torch.Tensor], spec: Spec, idx_state: Dict[str, torch.Tensor],
-            actions: Dict[str, torch.Tensor], eps: Dict[str, torch.Tensor]):
+            actions: Dict[str, torch.Tensor], eps: Dict[str, torch.Tensor], emulate_bf16: bool = False):
     """``MAVAE.forward`` with the normal draw made explicit.  Returns
     ``(recon_state[B,S], recon_reward[B,A], mu_all, log_var_all)``."""
+    q = emulate_bf16
     L = spec.latent
     n_enc = len(spec.enc_hidden) + 1
     n_dec = len(spec.dec_hidden) + 1
@@ -207,17 +229,18 @@ def forward(P: Dict[str, torch.Tensor], spec: Spec, idx_state: Dict[str, torch.T
     for a in idx_state.keys():
         x = idx_state[a].to(P["idx_emb.weight"].dtype)
         ids = x[:, 0].to(torch.int32).long()                     # model.py:142  .int()
-        h = torch.cat([torch.nn.functional.embedding(ids, P["idx_emb.weight"]), x[:, 1:]], dim=1)
-        lat = _mlp(P, f"encoders.{a}", n_enc, h)
+        h = _q(torch.cat([torch.nn.functional.embedding(ids, P["idx_emb.weight"]), x[:, 1:]], dim=1), q)
+        lat = _mlp(P, f"encoders.{a}", n_enc, h, q)
         mu, lv = lat[:, :L], lat[:, L:]                           # model.py:149-150
         z = mu + eps[a].to(mu.dtype) * torch.exp(0.5 * lv)        # model.py:77-81
         ai = actions[a].to(torch.int32).long().reshape(-1)        # model.py:146
         embs.append(torch.nn.functional.embedding(ai, P[f"action_encoder.{a}.weight"]))
         zs.append(z); mus.append(mu); lvs.append(lv)
-    dec_in = torch.cat(zs + embs, dim=-1)                          # model.py:158-164: all z, then all act-emb
-    recon_s = _mlp(P, "state_decoder", n_dec, dec_in)
-    r = _mlp(P, "reward_decoder", n_dec, dec_in)
-    recon_r = torch.nn.functional.linear(r, P["reward_linear.weight"], P["reward_linear.bias"])
+    dec_in = _q(torch.cat(zs + embs, dim=-1), q)                   # model.py:158-164: all z, then all act-emb
+    recon_s = _mlp(P, "state_decoder", n_dec, dec_in, q)
+    r = _mlp(P, "reward_decoder", n_dec, dec_in, q, out_fwd=True)
+    recon_r = _q(torch.nn.functional.linear(r, _q(P["reward_linear.weight"], q, True, False), P["reward_linear.bias"]),
+                 q, False, True)
     return recon_s, recon_r, mus, lvs
 
 
@@ -286,11 +309,11 @@ class OracleState:
 
 
 def grads(P, spec, idx_state, actions, eps, s_hat, r_hat, huber=True,
-          kl_weight=KL_WEIGHT, r_weight=R_WEIGHT):
+          kl_weight=KL_WEIGHT, r_weight=R_WEIGHT, emulate_bf16=False):
     """Forward + loss + autograd backward.  Returns (losses 4-tuple of floats, dict of grads for every
     tensor that took part, outputs)."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
-    rs, rr, mus, lvs = forward(leaves, spec, idx_state, actions, eps)
+    rs, rr, mus, lvs = forward(leaves, spec, idx_state, actions, eps, emulate_bf16)
     loss, sl, rl, kl = loss_s_r(rs, rr, s_hat.to(rs.dtype), r_hat.to(rs.dtype), mus, lvs, huber, kl_weight, r_weight)
     loss.backward()
     G = {k: v.grad for k, v in leaves.items() if v.grad is not None}

@@ -110,6 +110,17 @@ def main(case, precision, engine, mode="dropin", rng="eps"):
                 out["grad_rel_median"] = float(np.median(list(gerr.values())))
                 big = {k: v for k, v in gerr.items() if k.startswith(("state_decoder", "reward_decoder", "idx_emb", "reward_linear"))}
                 out["grad_rel_max_registered"] = max(big.values())
+                if precision == "bf16":
+                    # the same algorithm with the CUDA path's bf16 rounding points (oracle emulate_bf16): isolates kernel
+                    # errors from the ReLU-mask flips any bf16 evaluation shows against an fp32 run
+                    _, Gq, outs_q = O.grads(st.P, spec, idx_state, acts, eps, nxt, rew, huber, emulate_bf16=True)
+                    qerr = {k: rel_l2(p.grad, Gq[k]) for k, p in mine.items()}
+                    qw = max(qerr, key=qerr.get)
+                    out["grad_rel_max_vs_bf16_oracle"] = qerr[qw]; out["grad_rel_worst_vs_bf16_oracle"] = qw
+                    out["grad_rel_median_vs_bf16_oracle"] = float(np.median(list(qerr.values())))
+                    out["grad_rel_top_vs_bf16_oracle"] = sorted(((round(v, 6), k) for k, v in qerr.items()), reverse=True)[:6]
+                    out["recon_s_rel_vs_bf16_oracle"] = rel_l2(recon_s, outs_q[0])
+                    out["fp32_vs_bf16_oracle_grad_rel_max"] = max(rel_l2(Gq[k], G[k]) for k in mine)
                 gw = max(gold, key=gold.get)
                 out["golden_grad_err"] = gold[gw]; out["golden_grad_worst"] = gw
             opt.step()

@@ -56,11 +56,19 @@ def test_fp32_in_kernel_philox_draw():
 @pytest.mark.parametrize("engine", ["simt", "tcgen05"])
 @pytest.mark.parametrize("case", ["latent32", "default"])
 def test_bf16_step(case, engine):
+    """bf16 path.  Loss within 1e-3 of the reference (golden, identical weights).  Gradients are checked against the
+    oracle evaluated with the same bf16 rounding points (``emulate_bf16``): 1e-2 relative L2 per tensor (measured
+    ~2e-3; what remains is fp32 accumulation order flipping a handful of ReLU units).  Against the *fp32* oracle a
+    bf16 evaluation differs by up to ~13 % on the first decoder layers because ~0.3 % of ReLU units per layer
+    change sign under operand rounding — the CPU oracle in emulate_bf16 mode shows the same figure
+    (``fp32_vs_bf16_oracle_grad_rel_max``), so it is a property of bf16, not of the kernels."""
     o = run(case, "bf16", engine)
-    assert max(o["loss_rel_golden"][:1]) < 1e-3, o["loss_rel_golden"]       # step 1: identical weights
+    assert o["loss_rel_golden"][0] < 1e-3, o["loss_rel_golden"]
     assert max(o["recon_s_rel"], o["mu_rel"], o["logvar_rel"]) < 1e-2
-    assert o["grad_rel_max_registered"] < 2e-2, o
+    assert o["recon_s_rel_vs_bf16_oracle"] < 2e-3
+    assert o["grad_rel_max_vs_bf16_oracle"] < 1e-2, (o["grad_rel_worst_vs_bf16_oracle"], o["grad_rel_top_vs_bf16_oracle"])
     assert o["grad_rel_median"] < 2e-2
+    assert o["grad_rel_max"] < 1.5 * o["fp32_vs_bf16_oracle_grad_rel_max"] + 1e-2
 
 
 def test_bf16_tcgen05_fast_path():

@@ -320,7 +320,7 @@ def run_ours(args, w):
             roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
                     "traffic": None, "kernel": "gemm_tc_kernel (all %d GEMM launches of one step)" % len(rows),
                     "gemm_ms_per_step": tot_ms, "gemm_flop_per_step": tot_fl, "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
-                    "engine": bound, "top": rows[:8]}
+                    "engine": bound, "top": rows[:8], "all": rows}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on this box's host cores, bounded sample ----
     cpu = None

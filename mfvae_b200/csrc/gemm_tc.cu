@@ -136,93 +136,82 @@ template <int BN> struct TcCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;                     // 128 / 256 / 512: a power of two >= 32
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue staging*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // ------------------------------------------------------------------------------------------------
-// epilogue for one 32-row x 32-column chunk owned by one warp.
-// Phase 1: every lane (= one accumulator row) parks its 32 fp32 values in the warp's staging tile (row stride 36 words:
-//          conflict-free for 16-byte accesses).  Phase 2: the tile is re-read so that 8 lanes cover one row's 32 columns;
-//          bias / relu / relu-mask are applied there and every global access is a full 128-byte (fp32) or 64-byte (bf16)
-//          row segment instead of 32 row-strided 16-byte pieces.
+// epilogue for one 32-column chunk held by one thread (= one output row)
 // ------------------------------------------------------------------------------------------------
-constexpr int kStageLd = 36;                      // words per staged row
-constexpr int kStageWarpBytes = 32 * kStageLd * 4;
-
-__device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row_base, int col0, const uint32_t (&v)[32],
-                                               float* stage, int lane) {
-  float* mine = stage + lane * kStageLd;
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row, int col0, const uint32_t (&v)[32]) {
+  if (row >= p.M) return;
+  const int ncols = min(32, p.N - col0);
+  float f[32];
 #pragma unroll
-  for (int j = 0; j < 32; j += 4)
-    *reinterpret_cast<float4*>(mine + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                       __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-  __syncwarp();
-  const int cq = lane & 7, rsub = lane >> 3;
-  const int col = col0 + 4 * cq;
-  const int nvalid = min(4, p.N - col);
-  if (nvalid > 0) {
-    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool has_bias = (p.epi == kEpiBias || p.epi == kEpiBiasRelu);
-    if (has_bias) {
-      const float* b = p.bias + g * p.bias_gs + col;
-      if (nvalid == 4) b4 = *reinterpret_cast<const float4*>(b);
-      else { b4.x = b[0]; if (nvalid > 1) b4.y = b[1]; if (nvalid > 2) b4.z = b[2]; }
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (p.epi == kEpiBias || p.epi == kEpiBiasRelu) {
+    const float* b = p.bias + g * p.bias_gs + col0;
+    if (ncols == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 bb = *reinterpret_cast<const float4*>(b + j);
+        f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols) f[j] += b[j];
     }
+    if (p.epi == kEpiBiasRelu) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = rsub + 4 * i;
-      const int row = row_base + r;
-      if (row >= p.M) continue;
-      float4 x = *reinterpret_cast<const float4*>(stage + r * kStageLd + 4 * cq);
-      x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-      if (p.epi == kEpiBiasRelu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-      if (p.epi == kEpiReluMask) {
-        const __nv_bfloat16* a = p.aux + g * p.aux_gs + static_cast<long long>(row) * p.aux_ld + col;
-        float m0, m1 = 1.f, m2 = 1.f, m3 = 1.f;
-        if (nvalid == 4) {
-          const uint2 raw = *reinterpret_cast<const uint2*>(a);
-          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-          m0 = lo.x; m1 = lo.y; m2 = hi.x; m3 = hi.y;
-        } else {
-          m0 = __bfloat162float(a[0]);
-          if (nvalid > 1) m1 = __bfloat162float(a[1]);
-          if (nvalid > 2) m2 = __bfloat162float(a[2]);
-        }
-        if (!(m0 > 0.f)) x.x = 0.f;
-        if (!(m1 > 0.f)) x.y = 0.f;
-        if (!(m2 > 0.f)) x.z = 0.f;
-        if (!(m3 > 0.f)) x.w = 0.f;
-      }
-      if (p.c_dtype == kBF16) {
-        __nv_bfloat16* c = static_cast<__nv_bfloat16*>(p.C) + g * p.c_gs + static_cast<long long>(row) * p.c_ld + col;
-        if (nvalid == 4) {
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
-          uint2 o; o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(c) = o;
-        } else {
-          c[0] = __float2bfloat16_rn(x.x);
-          if (nvalid > 1) c[1] = __float2bfloat16_rn(x.y);
-          if (nvalid > 2) c[2] = __float2bfloat16_rn(x.z);
-        }
-      } else {
-        float* c = static_cast<float*>(p.C) + g * p.c_gs + static_cast<long long>(row) * p.c_ld + col;
-        if (p.accumulate_atomic) {
-          atomicAdd(c, x.x);
-          if (nvalid > 1) atomicAdd(c + 1, x.y);
-          if (nvalid > 2) atomicAdd(c + 2, x.z);
-          if (nvalid > 3) atomicAdd(c + 3, x.w);
-        } else if (nvalid == 4) {
-          *reinterpret_cast<float4*>(c) = x;
-        } else {
-          c[0] = x.x;
-          if (nvalid > 1) c[1] = x.y;
-          if (nvalid > 2) c[2] = x.z;
+      for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+  } else if (p.epi == kEpiReluMask) {
+    const __nv_bfloat16* a = p.aux + g * p.aux_gs + static_cast<long long>(row) * p.aux_ld + col0;
+    if (ncols == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(a + j);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 m = __bfloat1622float2(h[q]);
+          if (!(m.x > 0.f)) f[j + 2 * q] = 0.f;
+          if (!(m.y > 0.f)) f[j + 2 * q + 1] = 0.f;
         }
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols && !(__bfloat162float(a[j]) > 0.f)) f[j] = 0.f;
     }
   }
-  __syncwarp();
+  if (p.c_dtype == kBF16) {
+    __nv_bfloat16* c = static_cast<__nv_bfloat16*>(p.C) + g * p.c_gs + static_cast<long long>(row) * p.c_ld + col0;
+    if (ncols == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 o;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]), h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(c + j) = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols) c[j] = __float2bfloat16_rn(f[j]);
+    }
+  } else {
+    float* c = static_cast<float*>(p.C) + g * p.c_gs + static_cast<long long>(row) * p.c_ld + col0;
+    if (p.accumulate_atomic) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(c + j, f[j]);
+    } else if (ncols == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols) c[j] = f[j];
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -243,7 +232,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* acc_full = bars + 2 * kStages;                  // MMA -> epilogue   [2]
   uint64_t* acc_empty = bars + 2 * kStages + 2;             // epilogue -> MMA   [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  float* stage_all = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -342,8 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool has_k = ks * p.kb_per_split < p.k_blocks;
       mbar_wait(acc_full + as, aphase);
       tc_fence_after();
-      const int row_base = mt * BM + q * 32;
-      float* stage = stage_all + (warp - 2) * (kStageWarpBytes / 4);
+      const int row = mt * BM + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -352,7 +339,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
         tmem_ld_wait();
-        if (has_k) epilogue_chunk(p, g, row_base, col0, v, stage, lane);
+        if (has_k) epilogue_chunk(p, g, row, col0, v);
       }
       tc_fence_before();
       __syncwarp();

@@ -70,6 +70,11 @@ struct MfvaeHandle_ {
   int g_sout_fwd = -1, g_rout_fwd = -1, g_rl_fwd = -1;
   int g_sout_wg = -1, g_sout_dg = -1, g_rout_wg = -1, g_rout_dg = -1, g_rl_wg = -1, g_rl_dg = -1;
 
+  // side stream for the wgrad / bias-gradient chain of backward, with its fork / join events
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> fork_ev;
+  cudaEvent_t join_ev = nullptr;
+
   // optional per-GEMM event timing (bench.py roofline)
   bool profiling = false;
   std::vector<cudaEvent_t> prof_ev;          // 2 per GEMM op
@@ -417,34 +422,51 @@ static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStre
   return 0;
 }
 
+// Backward.  The dgrad chain (which carries the dependency from layer to layer) runs on the caller's stream; every
+// wgrad and bias column-sum only needs D_l and X_l, so they are forked onto a side stream as soon as D_l exists.  The
+// small layers of this network launch far fewer CTAs than the GPU has SMs; running the two chains concurrently fills
+// the machine.  Gradient-bucket events (data-parallel all-reduce) are recorded on the stream that finishes them.
 static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, const float* glat = nullptr, bool with_kl = true) {
   MFVAE_TRY(check_ready(h, b));
   const int dt = h->dtype, A = h->A, nh = h->cfg.n_dec_hidden;
   float* G = h->ar.d_grad;
   char* ws = h->ws;
+  const bool overlap = h->side != nullptr && !h->profiling;     // profiling wants serialised, undisturbed durations
+  cudaStream_t w = overlap ? h->side : s;                       // stream of the wgrad / colsum chain
+  size_t ev_i = 0;
+  auto fork = [&]() -> int {
+    if (!overlap) return 0;
+    MFVAE_CHECK(ev_i < h->fork_ev.size(), "fork event pool exhausted");
+    MFVAE_CUDA(cudaEventRecord(h->fork_ev[ev_i], s));
+    MFVAE_CUDA(cudaStreamWaitEvent(w, h->fork_ev[ev_i], 0));
+    ++ev_i;
+    return 0;
+  };
   // optimizer.zero_grad(): split-K wgrads and bias column sums accumulate with fp32 atomics
   MFVAE_CUDA(cudaMemsetAsync(G, 0, static_cast<size_t>(h->arena_elems) * sizeof(float), s));
-  // reward_linear + output layers
-  MFVAE_TRY(run_gemm(h, h->g_rl_wg, s));
-  MFVAE_TRY(launch_colsum(ws + h->DRR.off, dt, 1, h->B, A, h->DRR.ld, 0, G + h->rlb.off, 0, s));
-  MFVAE_TRY(run_gemm(h, h->g_rl_dg, s));
-  MFVAE_TRY(run_gemm(h, h->g_rout_wg, s));
-  MFVAE_TRY(launch_colsum(ws + h->DRR0.off, dt, 1, h->B, A, h->DRR0.ld, 0, G + h->rOutB.off, 0, s));
-  MFVAE_TRY(run_gemm(h, h->g_rout_dg, s));
-  MFVAE_TRY(run_gemm(h, h->g_sout_wg, s));
-  MFVAE_TRY(launch_colsum(ws + h->DRS.off, dt, 1, h->B, h->S, h->DRS.ld, 0, G + h->sOutB.off, 0, s));
+  MFVAE_TRY(fork());                                            // D(recon_s), D(recon_r) and the zeroed arena are ready
+  // output layers + reward_linear
+  MFVAE_TRY(run_gemm(h, h->g_sout_wg, w));
+  MFVAE_TRY(launch_colsum(ws + h->DRS.off, dt, 1, h->B, h->S, h->DRS.ld, 0, G + h->sOutB.off, 0, w));
+  MFVAE_TRY(run_gemm(h, h->g_rl_wg, w));
+  MFVAE_TRY(launch_colsum(ws + h->DRR.off, dt, 1, h->B, A, h->DRR.ld, 0, G + h->rlb.off, 0, w));
   MFVAE_TRY(run_gemm(h, h->g_sout_dg, s));
-  MFVAE_CUDA(cudaEventRecord(h->buckets[0].ev, s));
+  MFVAE_TRY(run_gemm(h, h->g_rl_dg, s));
+  MFVAE_TRY(fork());                                            // D(reward decoder output) ready
+  MFVAE_TRY(run_gemm(h, h->g_rout_wg, w));
+  MFVAE_TRY(launch_colsum(ws + h->DRR0.off, dt, 1, h->B, A, h->DRR0.ld, 0, G + h->rOutB.off, 0, w));
+  MFVAE_CUDA(cudaEventRecord(h->buckets[0].ev, w));
+  MFVAE_TRY(run_gemm(h, h->g_rout_dg, s));
   // decoder hidden layers, last to first
   for (int l = nh - 1; l >= 0; --l) {
-    MFVAE_TRY(run_gemm(h, h->g_dec_wg[l], s));
-    MFVAE_TRY(launch_colsum(ws + h->DHD[l].off, dt, 1, h->B, 2 * h->decH[l], h->DHD[l].ld, 0, G + h->decB[l].off, 0, s));
-    if (l == 1 || (l == 0 && nh == 1)) {}
+    MFVAE_TRY(fork());                                          // D_l (both decoder halves) ready
+    MFVAE_TRY(run_gemm(h, h->g_dec_wg[l], w));
+    MFVAE_TRY(launch_colsum(ws + h->DHD[l].off, dt, 1, h->B, 2 * h->decH[l], h->DHD[l].ld, 0, G + h->decB[l].off, 0, w));
+    if (l == 1) MFVAE_CUDA(cudaEventRecord(h->buckets[1].ev, w));
     MFVAE_TRY(run_gemm(h, h->g_dec_dg[l], s));
-    if (l == 1) MFVAE_CUDA(cudaEventRecord(h->buckets[1].ev, s));
   }
-  if (nh == 1) MFVAE_CUDA(cudaEventRecord(h->buckets[1].ev, s));
-  MFVAE_CUDA(cudaEventRecord(h->buckets[2].ev, s));
+  if (nh == 1) MFVAE_CUDA(cudaEventRecord(h->buckets[1].ev, w));
+  MFVAE_CUDA(cudaEventRecord(h->buckets[2].ev, w));
   // action tables (model.py:121: unregistered; gradients still flow)
   MFVAE_TRY(launch_act_table_grad(ws + h->GZIN.off, dt, h->GZIN.ld, A * h->L, b->d_act, A, h->d_meta + 2 * A, A, h->C, h->B,
                                   G + h->actT.off, static_cast<int64_t>(h->nact_max) * h->C, s));
@@ -462,8 +484,9 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
   // encoders, last layer to first
   for (int l = h->ne - 1; l >= 0; --l) {
     const MfvaeHandle_::Buf& D = (l + 1 == h->ne) ? h->DLAT : h->DXE[l];
-    MFVAE_TRY(run_gemm(h, h->g_enc_wg[l], s));
-    MFVAE_TRY(launch_colsum(ws + D.off, dt, A, h->B, h->encN[l], D.ld, D.gs, G + h->encB[l].off, h->encN[l], s));
+    MFVAE_TRY(fork());
+    MFVAE_TRY(run_gemm(h, h->g_enc_wg[l], w));
+    MFVAE_TRY(launch_colsum(ws + D.off, dt, A, h->B, h->encN[l], D.ld, D.gs, G + h->encB[l].off, h->encN[l], w));
     MFVAE_TRY(run_gemm(h, h->g_enc_dg[l], s));
   }
   // id embedding (model.py:113,142)
@@ -471,6 +494,10 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
     MFVAE_TRY(launch_idx_emb_scatter(ws + h->GX0.off, dt, h->GX0.gs, h->GX0.ld, b->d_idx, A, A, h->I, h->B, G + h->idx_emb.off, s));
   else
     MFVAE_TRY(launch_colsum(ws + h->GX0.off, dt, A, h->B, h->I, h->GX0.ld, h->GX0.gs, G + h->idx_emb.off, h->I, s));
+  if (overlap) {                                               // join
+    MFVAE_CUDA(cudaEventRecord(h->join_ev, w));
+    MFVAE_CUDA(cudaStreamWaitEvent(s, h->join_ev, 0));
+  }
   for (size_t i = 3; i < h->buckets.size(); ++i) MFVAE_CUDA(cudaEventRecord(h->buckets[i].ev, s));
   return 0;
 }
@@ -513,6 +540,13 @@ int mfvae_create(const MfvaeConfig* cfg, int device, MfvaeHandle* out) {
   add_bucket(0, h->reg2_begin);                       // idx_emb
   if (h->cfg.optimize_encoders) add_bucket(h->enc_begin, h->arena_elems);
   if (device < 0) { *out = h; return 0; }        // layout-only handle
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) h->side = nullptr;
+  for (int i = 0; i < 4 + 2 * MFVAE_MAX_HIDDEN + 4; ++i) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    h->fork_ev.push_back(e);
+  }
+  cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming);
   std::vector<int32_t> meta;
   meta.insert(meta.end(), h->obs_off.begin(), h->obs_off.end());
   meta.insert(meta.end(), h->obs_dim.begin(), h->obs_dim.end());
@@ -530,6 +564,9 @@ int mfvae_destroy(MfvaeHandle h) {
   free_plans(h);
   for (auto& b : h->buckets) if (b.ev) cudaEventDestroy(b.ev);
   for (auto e : h->prof_ev) cudaEventDestroy(e);
+  for (auto e : h->fork_ev) if (e) cudaEventDestroy(e);
+  if (h->join_ev) cudaEventDestroy(h->join_ev);
+  if (h->side) cudaStreamDestroy(h->side);
   if (h->d_meta) cudaFree(h->d_meta);
   delete h;
   return 0;

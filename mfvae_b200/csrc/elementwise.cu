@@ -72,13 +72,28 @@ __global__ void __launch_bounds__(kThreads) stage_kernel(StageArgs p) {
     int id = a;
     if (p.idx) id = static_cast<int>(p.idx[static_cast<int64_t>(b) * p.A + a]);
     float v[4];
+    if (c0 >= p.I && c0 + 3 < p.I + od) {
+      // interior strip of the observation: widest aligned load the agent's column offset allows
+      const float* src = p.obs + static_cast<int64_t>(b) * p.obs_ld + off + (c0 - p.I);
+      const uintptr_t ad = reinterpret_cast<uintptr_t>(src);
+      if ((ad & 15) == 0) {
+        const float4 t = ldg_stream4(src);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else if ((ad & 7) == 0) {
+        const float2 t0 = __ldg(reinterpret_cast<const float2*>(src)), t1 = __ldg(reinterpret_cast<const float2*>(src) + 1);
+        v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+      } else {
+        v[0] = __ldg(src); v[1] = __ldg(src + 1); v[2] = __ldg(src + 2); v[3] = __ldg(src + 3);
+      }
+    } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = c0 + k;
-      float x = 0.f;
-      if (c < p.I) x = p.idx_emb[static_cast<int64_t>(id) * p.I + c];
-      else if (c < p.I + od) x = __ldg(p.obs + static_cast<int64_t>(b) * p.obs_ld + off + (c - p.I));
-      v[k] = x;
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + k;
+        float x = 0.f;
+        if (c < p.I) x = p.idx_emb[static_cast<int64_t>(id) * p.I + c];
+        else if (c < p.I + od) x = __ldg(p.obs + static_cast<int64_t>(b) * p.obs_ld + off + (c - p.I));
+        v[k] = x;
+      }
     }
     store4<T>(x0 + a * p.x0_gs + static_cast<int64_t>(b) * p.x0_ld + c0, make_float4(v[0], v[1], v[2], v[3]));
   }
@@ -298,47 +313,75 @@ int launch_recon_loss(const ReconLossArgs& a, cudaStream_t s) {
 
 // ---------------------------------------------------------------------------------------------
 // column sums (bias gradients): out[g][n] += sum_b X[g][b][n]
-// block = 32 (column pairs) x 8 (row phases); grid = (col tiles, row splits, groups)
+// One thread owns a 4-column strip (8-byte bf16 / 16-byte fp32 loads); a warp covers LPR strips of one row and
+// 32 / LPR consecutive rows per load instruction, 4 independent loads in flight per thread.  Partial sums are folded
+// across the CTA in shared memory and leave with one fp32 atomic per column per CTA.
+// grid = (column tiles of 4 * LPR, row splits, groups); block = 256.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int LPR>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int64_t B, int N, int64_t ld,
                                                      int64_t gs, float* __restrict__ out, int64_t out_gs) {
-  __shared__ float sm[8][64];
+  constexpr int RPB = 256 / LPR;                  // rows covered by the CTA per pass
+  __shared__ float4 sm[256];
   const int g = blockIdx.z;
-  const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
+  const int strip = threadIdx.x % LPR, rphase = threadIdx.x / LPR;
+  const int c = (blockIdx.x * LPR + strip) * 4;
   const T* xg = x + g * gs;
-  float s0 = 0.f, s1 = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c < N) {
-    const bool two = (c + 1 < N);
-    for (int64_t b = blockIdx.y * 8 + threadIdx.y; b < B; b += static_cast<int64_t>(gridDim.y) * 8) {
-      const T* row = xg + b * ld + c;
-      s0 += to_f<T>(row[0]);
-      if (two) s1 += to_f<T>(row[1]);
+    const int64_t stride = static_cast<int64_t>(gridDim.y) * RPB;
+    int64_t b = static_cast<int64_t>(blockIdx.y) * RPB + rphase;
+    for (; b + 3 * stride < B; b += 4 * stride) {
+      const float4 v0 = load4<T>(xg + b * ld + c);
+      const float4 v1 = load4<T>(xg + (b + stride) * ld + c);
+      const float4 v2 = load4<T>(xg + (b + 2 * stride) * ld + c);
+      const float4 v3 = load4<T>(xg + (b + 3 * stride) * ld + c);
+      acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+      acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; b < B; b += stride) {
+      const float4 v = load4<T>(xg + b * ld + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
-  sm[threadIdx.y][threadIdx.x * 2] = s0;
-  sm[threadIdx.y][threadIdx.x * 2 + 1] = s1;
+  sm[threadIdx.x] = acc;
   __syncthreads();
-  if (threadIdx.y == 0) {
-#pragma unroll
-    for (int k = 1; k < 8; ++k) { s0 += sm[k][threadIdx.x * 2]; s1 += sm[k][threadIdx.x * 2 + 1]; }
-    if (c < N) atomicAdd(out + g * out_gs + c, s0);
-    if (c + 1 < N) atomicAdd(out + g * out_gs + c + 1, s1);
+  if (rphase == 0 && c < N) {
+#pragma unroll 4
+    for (int r = 1; r < RPB; ++r) {
+      const float4 v = sm[r * LPR + strip];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float* o = out + g * out_gs + c;
+    atomicAdd(o, acc.x);
+    if (c + 1 < N) atomicAdd(o + 1, acc.y);
+    if (c + 2 < N) atomicAdd(o + 2, acc.z);
+    if (c + 3 < N) atomicAdd(o + 3, acc.w);
   }
+}
+
+template <typename T>
+static int colsum_dispatch(const T* x, int G, int64_t B, int N, int64_t ld, int64_t gs, float* out, int64_t out_gs, cudaStream_t s) {
+  // columns are read 4 at a time: the padded row (ld, a multiple of 8) always holds whole strips
+  const int strips = (N + 3) / 4;
+  const int lpr = strips >= 32 ? 32 : (strips > 8 ? 16 : 8);
+  const int ctiles = (strips + lpr - 1) / lpr;
+  const int rpb = 256 / lpr;
+  const int64_t want = (static_cast<int64_t>(kNumSMs) * 4) / std::max<int64_t>(1, static_cast<int64_t>(ctiles) * G);
+  const int splits = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, (B + 4 * rpb - 1) / (4 * rpb))));
+  dim3 grid(ctiles, splits, G);
+  if (lpr == 32) colsum_kernel<T, 32><<<grid, 256, 0, s>>>(x, B, N, ld, gs, out, out_gs);
+  else if (lpr == 16) colsum_kernel<T, 16><<<grid, 256, 0, s>>>(x, B, N, ld, gs, out, out_gs);
+  else colsum_kernel<T, 8><<<grid, 256, 0, s>>>(x, B, N, ld, gs, out, out_gs);
+  MFVAE_LAUNCH_CHECK();
+  return 0;
 }
 
 int launch_colsum(const void* x, int dtype, int G, int64_t B, int N, int64_t ld, int64_t gs,
                   float* out, int64_t out_gs, cudaStream_t s) {
-  const int ctiles = (N + 63) / 64;
-  int64_t want = (static_cast<int64_t>(kNumSMs) * 4) / (static_cast<int64_t>(ctiles) * G);
-  int splits = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, (B + 63) / 64)));
-  dim3 grid(ctiles, splits, G), block(32, 8);
-  if (dtype == kBF16)
-    colsum_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(static_cast<const __nv_bfloat16*>(x), B, N, ld, gs, out, out_gs);
-  else
-    colsum_kernel<float><<<grid, block, 0, s>>>(static_cast<const float*>(x), B, N, ld, gs, out, out_gs);
-  MFVAE_LAUNCH_CHECK();
-  return 0;
+  MFVAE_CHECK(ld % 4 == 0 && gs % 4 == 0 && ld >= (N + 3) / 4 * 4, "colsum: rows must be padded to whole 4-column strips");
+  if (dtype == kBF16) return colsum_dispatch(static_cast<const __nv_bfloat16*>(x), G, B, N, ld, gs, out, out_gs, s);
+  return colsum_dispatch(static_cast<const float*>(x), G, B, N, ld, gs, out, out_gs, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -398,10 +441,75 @@ __global__ void __launch_bounds__(kThreads) act_table_grad_kernel(const T* __res
   for (int i = threadIdx.x; i < na * C; i += blockDim.x) atomicAdd(d_table + a * table_gs + i, acc[i]);
 }
 
+// Few actions (Discrete(5) in simple_tag): every thread owns 4 columns of one agent and keeps one running sum per
+// action in registers (predicated adds, no shared-memory atomics); rows are strided over (blockIdx.x, row phase).
+// grid = (row chunks, A); block = 256 = (C / 4 strips) x (256 / (C / 4) row phases)
+template <typename T, int NA>
+__global__ void __launch_bounds__(kThreads) act_table_grad_small_kernel(const T* __restrict__ gzin, int64_t ld, int col0,
+                                                                        const float* __restrict__ act, int act_ld,
+                                                                        const int32_t* __restrict__ n_act, int C, int64_t B,
+                                                                        float* __restrict__ d_table, int64_t table_gs) {
+  const int a = blockIdx.y;
+  const int strips = C / 4;
+  const int strip = threadIdx.x % strips, rphase = threadIdx.x / strips;
+  const int rpb = blockDim.x / strips;
+  const int na = n_act[a];
+  float4 acc[NA];
+#pragma unroll
+  for (int k = 0; k < NA; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rphase < rpb) {
+    for (int64_t b = static_cast<int64_t>(blockIdx.x) * rpb + rphase; b < B; b += static_cast<int64_t>(gridDim.x) * rpb) {
+      int kk = static_cast<int>(__ldg(act + b * act_ld + a));
+      kk = max(0, min(kk, na - 1));
+      const float4 v = load4<T>(gzin + b * ld + col0 + a * C + strip * 4);
+#pragma unroll
+      for (int k = 0; k < NA; ++k) {
+        const float m = (kk == k) ? 1.f : 0.f;
+        acc[k].x = fmaf(m, v.x, acc[k].x); acc[k].y = fmaf(m, v.y, acc[k].y);
+        acc[k].z = fmaf(m, v.z, acc[k].z); acc[k].w = fmaf(m, v.w, acc[k].w);
+      }
+    }
+    // fold the row phases of a warp that share a strip (strips divides 32 or is a multiple of it)
+    for (int o = 16; o >= strips && o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < NA; ++k) {
+        acc[k].x += __shfl_down_sync(0xffffffffu, acc[k].x, o); acc[k].y += __shfl_down_sync(0xffffffffu, acc[k].y, o);
+        acc[k].z += __shfl_down_sync(0xffffffffu, acc[k].z, o); acc[k].w += __shfl_down_sync(0xffffffffu, acc[k].w, o);
+      }
+    }
+    const bool leader = (strips >= 32) || ((threadIdx.x & 31) < strips);
+    if (leader) {
+#pragma unroll
+      for (int k = 0; k < NA; ++k) {
+        if (k < na) {
+          float* o = d_table + a * table_gs + static_cast<int64_t>(k) * C + strip * 4;
+          atomicAdd(o, acc[k].x); atomicAdd(o + 1, acc[k].y); atomicAdd(o + 2, acc[k].z); atomicAdd(o + 3, acc[k].w);
+        }
+      }
+    }
+  }
+}
+
 int launch_act_table_grad(const void* gzin, int dtype, int64_t ld, int col0, const float* act, int act_ld,
                           const int32_t* n_act, int A, int C, int64_t B, float* d_table, int64_t table_gs,
                           cudaStream_t s) {
   MFVAE_CHECK(C <= kThreads, "act_table_grad: act_features must be <= 256");
+  const int na_max = static_cast<int>(table_gs / C);
+  const int strips = C / 4;
+  const bool small = na_max <= 8 && C % 4 == 0 && ld % 4 == 0 && col0 % 4 == 0 && (strips >= 32 ? strips % 32 == 0 : 32 % strips == 0) &&
+                     strips <= kThreads;
+  if (small) {
+    const int rpb = kThreads / strips;
+    int chunks = static_cast<int>(std::min<int64_t>((B + rpb * 8 - 1) / (rpb * 8), std::max(1, kNumSMs * 8 / A)));
+    chunks = std::max(chunks, 1);
+    dim3 grid(chunks, A);
+    if (dtype == kBF16)
+      act_table_grad_small_kernel<__nv_bfloat16, 8><<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(gzin), ld, col0, act, act_ld, n_act, C, B, d_table, table_gs);
+    else
+      act_table_grad_small_kernel<float, 8><<<grid, kThreads, 0, s>>>(static_cast<const float*>(gzin), ld, col0, act, act_ld, n_act, C, B, d_table, table_gs);
+    MFVAE_LAUNCH_CHECK();
+    return 0;
+  }
   MFVAE_CHECK(table_gs * sizeof(float) <= 48 * 1024, "act_table_grad: action table too large for the shared-memory path");
   const int rows_per_iter = kThreads / C;
   int chunks = static_cast<int>(std::min<int64_t>((B + rows_per_iter * 8 - 1) / (rows_per_iter * 8),

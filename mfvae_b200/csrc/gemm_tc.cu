@@ -9,11 +9,12 @@
 //   wgrad    dW = dY^T X      A = dY (MN-major)  B = X (MN-major)       epilogue: fp32 (+= with split-K)
 // so no operand is ever transposed in HBM: the UMMA shared-memory descriptors take either major.
 //
-// CTA = 6 warps, persistent over a static round-robin tile schedule:
+// CTA = 10 warps, persistent over a static round-robin tile schedule:
 //   warp 0      TMA producer   (one lane): cp.async.bulk.tensor.3d into a kStages-deep 128B-swizzled ring
 //   warp 1      MMA issuer     (one lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 per instruction;
 //                              tcgen05.commit releases ring slots and publishes finished accumulators
-//   warps 2..5  epilogue       tcgen05.ld 32 lanes x 32 columns -> registers -> bias/relu/mask -> global
+//   warps 2..9  epilogue       tcgen05.ld 32 lanes x 32 columns -> registers -> bias/relu/mask -> global
+//                              (two warps per TMEM lane quarter, next chunk's TMEM load overlapped with the stores)
 // TMEM holds two accumulator stages (2 x BN fp32 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 
@@ -27,7 +28,8 @@ namespace mfvae {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                    // 64 bf16 = 128 bytes = one SWIZZLE_128B row
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8;               // two warps per TMEM lane quarter: they split the column chunks
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kSpinLimit = 1u << 26; // bounded waits: a protocol bug traps instead of hanging the GPU
 
 struct TcParams {
@@ -244,7 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a); prefetch_tmap(&map_b);
     for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -324,29 +326,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    // Warp (2 + i) may only touch TMEM lanes 32 * ((2 + i) & 3) ...; the two warps of a quarter take alternate
+    // 32-column chunks.  The TMEM load of the next chunk is in flight while the current one is converted and stored.
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;              // 0 or 1
     int as = 0; uint32_t aphase = 0;
     for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const int nt = static_cast<int>(w % p.n_tiles);
       const int mt = static_cast<int>((w / p.n_tiles) % p.m_tiles);
       const long long r = w / tiles_per_split;
-      const int ks = static_cast<int>(r % p.splits);
       const int g = static_cast<int>(r / p.splits);
-      const bool has_k = ks * p.kb_per_split < p.k_blocks;
       mbar_wait(acc_full + as, aphase);
       tc_fence_after();
       const int row = mt * BM + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+      constexpr int kChunks = BN / 32;
+      const int ncols_tile = min(BN, p.N - nt * BN);
+      const int nchunks = (ncols_tile + 31) / 32;
+      uint32_t va[32], vb[32];
+      int c = half;
+      if (c < nchunks) tmem_ld32(taddr + c * 32, va);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = nt * BN + c * 32;
-        if (col0 >= p.N) break;
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
+      for (; c < nchunks; c += 4) {
         tmem_ld_wait();
-        if (has_k) epilogue_chunk(p, g, row, col0, v);
+        const bool more = (c + 2) < nchunks;
+        if (more) tmem_ld32(taddr + (c + 2) * 32, vb);
+        epilogue_chunk(p, g, row, nt * BN + c * 32, va);
+        if (more) {
+          tmem_ld_wait();
+          if (c + 4 < nchunks) tmem_ld32(taddr + (c + 4) * 32, va);
+          epilogue_chunk(p, g, row, nt * BN + (c + 2) * 32, vb);
+        }
       }
+      (void)kChunks;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + as);

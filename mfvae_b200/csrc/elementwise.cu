@@ -56,46 +56,48 @@ __device__ __forceinline__ void finish_scalar(float block_total, float* scratch,
 // stage: packed fp32 rows -> encoder input X0[a][b][:] = [idx_emb[id] | obs_a | 0] and the action-embedding
 // half of the decoder input.
 // ---------------------------------------------------------------------------------------------
+// grid = (row chunks, A); block = 256 threads = (256 / VL) rows x VL column strips of 4
 template <typename T>
 __global__ void __launch_bounds__(kThreads) stage_kernel(StageArgs p) {
+  const int a = blockIdx.y;
   const int nvec = p.x0_ld / 4;
-  const int64_t per_agent = static_cast<int64_t>(p.B) * nvec;
-  const int64_t total = per_agent * p.A;
-  T* x0 = static_cast<T*>(p.x0);
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int a = static_cast<int>(i / per_agent);
-    const int64_t r = i - a * per_agent;
-    const int b = static_cast<int>(r / nvec);
-    const int c0 = static_cast<int>(r - static_cast<int64_t>(b) * nvec) * 4;
-    const int od = p.obs_dim[a], off = p.obs_off[a];
+  const int VL = nvec <= 32 ? 32 : (nvec <= 64 ? 64 : 128);      // strips handled per row pass
+  const int rows_per_pass = kThreads / VL;
+  const int strip0 = threadIdx.x % VL, rphase = threadIdx.x / VL;
+  const int od = p.obs_dim[a], off = p.obs_off[a];
+  T* x0 = static_cast<T*>(p.x0) + a * p.x0_gs;
+  for (int b = blockIdx.x * rows_per_pass + rphase; b < p.B; b += gridDim.x * rows_per_pass) {
     int id = a;
     if (p.idx) id = static_cast<int>(p.idx[static_cast<int64_t>(b) * p.A + a]);
-    float v[4];
-    if (c0 >= p.I && c0 + 3 < p.I + od) {
-      // interior strip of the observation: widest aligned load the agent's column offset allows
-      const float* src = p.obs + static_cast<int64_t>(b) * p.obs_ld + off + (c0 - p.I);
-      const uintptr_t ad = reinterpret_cast<uintptr_t>(src);
-      if ((ad & 15) == 0) {
-        const float4 t = ldg_stream4(src);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-      } else if ((ad & 7) == 0) {
-        const float2 t0 = __ldg(reinterpret_cast<const float2*>(src)), t1 = __ldg(reinterpret_cast<const float2*>(src) + 1);
-        v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+    const float* orow = p.obs + static_cast<int64_t>(b) * p.obs_ld + off;
+    for (int strip = strip0; strip < nvec; strip += VL) {
+      const int c0 = strip * 4;
+      float v[4];
+      if (c0 >= p.I && c0 + 3 < p.I + od) {
+        // interior strip of the observation: widest aligned load the agent's column offset allows
+        const float* src = orow + (c0 - p.I);
+        const uintptr_t ad = reinterpret_cast<uintptr_t>(src);
+        if ((ad & 15) == 0) {
+          const float4 t = ldg_stream4(src);
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else if ((ad & 7) == 0) {
+          const float2 t0 = __ldg(reinterpret_cast<const float2*>(src)), t1 = __ldg(reinterpret_cast<const float2*>(src) + 1);
+          v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+        } else {
+          v[0] = __ldg(src); v[1] = __ldg(src + 1); v[2] = __ldg(src + 2); v[3] = __ldg(src + 3);
+        }
       } else {
-        v[0] = __ldg(src); v[1] = __ldg(src + 1); v[2] = __ldg(src + 2); v[3] = __ldg(src + 3);
-      }
-    } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c = c0 + k;
-        float x = 0.f;
-        if (c < p.I) x = p.idx_emb[static_cast<int64_t>(id) * p.I + c];
-        else if (c < p.I + od) x = __ldg(p.obs + static_cast<int64_t>(b) * p.obs_ld + off + (c - p.I));
-        v[k] = x;
+        for (int k = 0; k < 4; ++k) {
+          const int c = c0 + k;
+          float x = 0.f;
+          if (c < p.I) x = p.idx_emb[static_cast<int64_t>(id) * p.I + c];
+          else if (c < p.I + od) x = __ldg(orow + (c - p.I));
+          v[k] = x;
+        }
       }
+      store4<T>(x0 + static_cast<int64_t>(b) * p.x0_ld + c0, make_float4(v[0], v[1], v[2], v[3]));
     }
-    store4<T>(x0 + a * p.x0_gs + static_cast<int64_t>(b) * p.x0_ld + c0, make_float4(v[0], v[1], v[2], v[3]));
   }
 }
 
@@ -122,11 +124,16 @@ int launch_stage(const StageArgs& a, cudaStream_t s) {
   MFVAE_CHECK(a.x0_ld % 4 == 0 && a.C % 4 == 0 && a.zin_ld % 4 == 0, "stage: widths must be multiples of 4");
   const int64_t t0 = static_cast<int64_t>(a.A) * a.B * (a.x0_ld / 4);
   const int64_t t1 = static_cast<int64_t>(a.A) * a.B * (a.C / 4);
+  (void)t0;
+  const int nvec = a.x0_ld / 4;
+  const int rpp = kThreads / (nvec <= 32 ? 32 : (nvec <= 64 ? 64 : 128));
+  const int chunks = std::max(1, std::min((a.B + rpp * 4 - 1) / (rpp * 4), std::max(1, kNumSMs * 16 / a.A)));
+  dim3 sgrid(chunks, a.A);
   if (a.dtype == kBF16) {
-    stage_kernel<__nv_bfloat16><<<grid_for(t0), kThreads, 0, s>>>(a);
+    stage_kernel<__nv_bfloat16><<<sgrid, kThreads, 0, s>>>(a);
     act_embed_kernel<__nv_bfloat16><<<grid_for(t1), kThreads, 0, s>>>(a);
   } else {
-    stage_kernel<float><<<grid_for(t0), kThreads, 0, s>>>(a);
+    stage_kernel<float><<<sgrid, kThreads, 0, s>>>(a);
     act_embed_kernel<float><<<grid_for(t1), kThreads, 0, s>>>(a);
   }
   ++g_launch_count;
@@ -148,11 +155,12 @@ __global__ void __launch_bounds__(kThreads) reparam_kl_fwd_kernel(ReparamArgs p)
   float acc = 0.f;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int jq = static_cast<int>(i % lq);
-    const int64_t r = i / lq;
+    // (sample, agent) pairs fit 32 bits (checked by the launcher): cheap unsigned division instead of 64-bit
+    const uint32_t pr = static_cast<uint32_t>(i / lq);
+    const int jq = static_cast<int>(i - static_cast<int64_t>(pr) * lq);
     int a; int64_t b;
-    if (AGENT_MAJOR) { b = r % p.B; a = static_cast<int>(r / p.B); }
-    else             { a = static_cast<int>(r % p.A); b = r / p.A; }
+    if (AGENT_MAJOR) { const uint32_t B32 = static_cast<uint32_t>(p.B); a = static_cast<int>(pr / B32); b = pr - static_cast<uint32_t>(a) * B32; }
+    else             { const uint32_t A32 = static_cast<uint32_t>(p.A); b = pr / A32; a = static_cast<int>(pr - static_cast<uint32_t>(b) * A32); }
     const int64_t off = a * p.lat_as + b * p.lat_bs + jq * 4;
     const float4 mu = ldg_stream4(p.mu + off);
     const float4 lv = ldg_stream4(p.lv + off);
@@ -177,6 +185,7 @@ __global__ void __launch_bounds__(kThreads) reparam_kl_fwd_kernel(ReparamArgs p)
 int launch_reparam_kl_fwd(const ReparamArgs& a, cudaStream_t s) {
   MFVAE_CHECK(a.L % 4 == 0, "reparam: latent must be a multiple of 4");
   MFVAE_CHECK(a.lat_as % 4 == 0 && a.lat_bs % 4 == 0 && a.z_ld % 4 == 0, "reparam: strides must be multiples of 4");
+  MFVAE_CHECK(a.B * a.A < (1LL << 31), "reparam: batch * agents must fit 31 bits");
   const int64_t total = a.B * a.A * (a.L / 4);
   const int grid = grid_for(total);
   const bool am = a.lat_as > a.lat_bs;
@@ -199,10 +208,11 @@ __global__ void __launch_bounds__(kThreads) reparam_kl_bwd_kernel(ReparamBwdArgs
   TD* dl = static_cast<TD*>(p.dlat);
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int jq = static_cast<int>(i % lq);
-    const int64_t r = i / lq;
-    const int64_t b = r % p.B;
-    const int a = static_cast<int>(r / p.B);
+    const uint32_t pr = static_cast<uint32_t>(i / lq);
+    const int jq = static_cast<int>(i - static_cast<int64_t>(pr) * lq);
+    const uint32_t B32 = static_cast<uint32_t>(p.B);
+    const int a = static_cast<int>(pr / B32);
+    const int64_t b = pr - static_cast<uint32_t>(a) * B32;
     const int64_t off = a * p.lat_as + b * p.lat_bs + jq * 4;
     const float4 mu = *reinterpret_cast<const float4*>(p.mu + off);
     const float4 lv = *reinterpret_cast<const float4*>(p.lv + off);
@@ -233,6 +243,7 @@ __global__ void __launch_bounds__(kThreads) reparam_kl_bwd_kernel(ReparamBwdArgs
 int launch_reparam_kl_bwd(const ReparamBwdArgs& a, cudaStream_t s) {
   MFVAE_CHECK(a.L % 4 == 0 && a.gz_ld % 4 == 0 && a.dlat_bs % 4 == 0, "reparam bwd: widths must be multiples of 4");
   MFVAE_CHECK(a.g_dtype == a.d_dtype, "reparam bwd: mixed dtypes unsupported");
+  MFVAE_CHECK(a.B * a.A < (1LL << 31), "reparam bwd: batch * agents must fit 31 bits");
   const int grid = grid_for(a.B * a.A * (a.L / 4));
   if (a.g_dtype == kBF16) reparam_kl_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kThreads, 0, s>>>(a);
   else                    reparam_kl_bwd_kernel<float, float><<<grid, kThreads, 0, s>>>(a);
@@ -469,23 +480,23 @@ __global__ void __launch_bounds__(kThreads) act_table_grad_small_kernel(const T*
         acc[k].z = fmaf(m, v.z, acc[k].z); acc[k].w = fmaf(m, v.w, acc[k].w);
       }
     }
-    // fold the row phases of a warp that share a strip (strips divides 32 or is a multiple of it)
-    for (int o = 16; o >= strips && o > 0; o >>= 1) {
+  }
+  // fold every row phase of the CTA that shares a strip through shared memory, then one atomic per (action, column)
+  __shared__ float4 fold[kThreads];
 #pragma unroll
-      for (int k = 0; k < NA; ++k) {
-        acc[k].x += __shfl_down_sync(0xffffffffu, acc[k].x, o); acc[k].y += __shfl_down_sync(0xffffffffu, acc[k].y, o);
-        acc[k].z += __shfl_down_sync(0xffffffffu, acc[k].z, o); acc[k].w += __shfl_down_sync(0xffffffffu, acc[k].w, o);
+  for (int k = 0; k < NA; ++k) {
+    if (k >= na) break;                     // uniform across the CTA (one agent per CTA)
+    __syncthreads();
+    fold[threadIdx.x] = acc[k];
+    __syncthreads();
+    if (rphase == 0) {
+      float4 t = fold[strip];
+      for (int r = 1; r < rpb; ++r) {
+        const float4 u = fold[r * strips + strip];
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
       }
-    }
-    const bool leader = (strips >= 32) || ((threadIdx.x & 31) < strips);
-    if (leader) {
-#pragma unroll
-      for (int k = 0; k < NA; ++k) {
-        if (k < na) {
-          float* o = d_table + a * table_gs + static_cast<int64_t>(k) * C + strip * 4;
-          atomicAdd(o, acc[k].x); atomicAdd(o + 1, acc[k].y); atomicAdd(o + 2, acc[k].z); atomicAdd(o + 3, acc[k].w);
-        }
-      }
+      float* o = d_table + a * table_gs + static_cast<int64_t>(k) * C + strip * 4;
+      atomicAdd(o, t.x); atomicAdd(o + 1, t.y); atomicAdd(o + 2, t.z); atomicAdd(o + 3, t.w);
     }
   }
 }
@@ -500,7 +511,7 @@ int launch_act_table_grad(const void* gzin, int dtype, int64_t ld, int col0, con
                      strips <= kThreads;
   if (small) {
     const int rpb = kThreads / strips;
-    int chunks = static_cast<int>(std::min<int64_t>((B + rpb * 8 - 1) / (rpb * 8), std::max(1, kNumSMs * 8 / A)));
+    int chunks = static_cast<int>(std::min<int64_t>((B + rpb * 8 - 1) / (rpb * 8), std::max(1, kNumSMs * 2 / A)));
     chunks = std::max(chunks, 1);
     dim3 grid(chunks, A);
     if (dtype == kBF16)

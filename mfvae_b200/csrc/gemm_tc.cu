@@ -28,8 +28,14 @@ namespace mfvae {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                    // 64 bf16 = 128 bytes = one SWIZZLE_128B row
-constexpr int kEpiWarps = 8;               // two warps per TMEM lane quarter: they split the column chunks
-constexpr int kTcThreads = 64 + 32 * kEpiWarps;
+// Two launch shapes.  CPS = CTAs per SM:
+//   CPS = 1  deep ring (up to 8 stages), 8 epilogue warps (two per TMEM lane quarter)  -> K-long, tensor-bound GEMMs
+//   CPS = 3  3-stage ring of 24 KB (BN = 64), 4 epilogue warps, <= 112 registers        -> K <= 256 GEMMs, whose tiles
+//            are 1-4 MMAs followed by an epilogue: three co-resident CTAs hide each other's TMEM / store latency
+template <int CPS> struct TcShape {
+  static constexpr int kEpiWarps = (CPS == 1) ? 8 : 4;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+};
 constexpr uint32_t kSpinLimit = 1u << 26; // bounded waits: a protocol bug traps instead of hanging the GPU
 
 struct TcParams {
@@ -132,11 +138,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool 
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-template <int BN> struct TcCfg {
+template <int BN, int CPS> struct TcCfg {
   static constexpr int kABytes = BM * BK * 2;                  // 16 KB
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+  static constexpr int kStagesDeep = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+  static constexpr int kStages = (CPS == 1) ? kStagesDeep : 3;
   static constexpr int kTmemCols = 2 * BN;                     // 128 / 256 / 512: a power of two >= 32
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -225,10 +232,11 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int BN, bool A_MN, bool B_MN, int CPS>
+__global__ void __launch_bounds__(TcShape<CPS>::kThreads, CPS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, CPS>;
+  constexpr int kEpiWarps = TcShape<CPS>::kEpiWarps;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -330,7 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // Warp (2 + i) may only touch TMEM lanes 32 * ((2 + i) & 3) ...; the two warps of a quarter take alternate
     // 32-column chunks.  The TMEM load of the next chunk is in flight while the current one is converted and stored.
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;              // 0 or 1
+    const int half = (warp - 2) >> 2;              // which of the quarter's warps (0 .. kEpiWarps/4 - 1)
     int as = 0; uint32_t aphase = 0;
     for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const int nt = static_cast<int>(w % p.n_tiles);
@@ -344,19 +352,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr int kChunks = BN / 32;
       const int ncols_tile = min(BN, p.N - nt * BN);
       const int nchunks = (ncols_tile + 31) / 32;
-      uint32_t va[32], vb[32];
-      int c = half;
-      if (c < nchunks) tmem_ld32(taddr + c * 32, va);
+      if constexpr (kEpiWarps == 8) {
+        uint32_t va[32], vb[32];
+        int c = half;
+        if (c < nchunks) tmem_ld32(taddr + c * 32, va);
 #pragma unroll 1
-      for (; c < nchunks; c += 4) {
-        tmem_ld_wait();
-        const bool more = (c + 2) < nchunks;
-        if (more) tmem_ld32(taddr + (c + 2) * 32, vb);
-        epilogue_chunk(p, g, row, nt * BN + c * 32, va);
-        if (more) {
+        for (; c < nchunks; c += 4) {
           tmem_ld_wait();
-          if (c + 4 < nchunks) tmem_ld32(taddr + (c + 4) * 32, va);
-          epilogue_chunk(p, g, row, nt * BN + (c + 2) * 32, vb);
+          const bool more = (c + 2) < nchunks;
+          if (more) tmem_ld32(taddr + (c + 2) * 32, vb);
+          epilogue_chunk(p, g, row, nt * BN + c * 32, va);
+          if (more) {
+            tmem_ld_wait();
+            if (c + 4 < nchunks) tmem_ld32(taddr + (c + 4) * 32, va);
+            epilogue_chunk(p, g, row, nt * BN + (c + 2) * 32, vb);
+          }
+        }
+      } else {
+        uint32_t va[32];
+#pragma unroll 1
+        for (int c = 0; c < nchunks; ++c) {
+          tmem_ld32(taddr + c * 32, va);
+          tmem_ld_wait();
+          epilogue_chunk(p, g, row, nt * BN + c * 32, va);
         }
       }
       (void)kChunks;
@@ -396,6 +414,7 @@ struct TcPlan {
   TcParams prm;
   CUtensorMap map_a, map_b;
   int BN = 0; bool a_mn = false, b_mn = false;
+  int cps = 1;                // CTAs per SM of the chosen launch shape
   int grid = 0;
 };
 
@@ -425,11 +444,12 @@ static int encode_operand(CUtensorMap* map, const void* base, int rows, int K, i
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CPS>
 static int launch_tc(const TcPlan* pl, cudaStream_t s) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, CPS>;
+  constexpr int kTcThreads = TcShape<CPS>::kThreads;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CPS>;
   if (!attr_set) {
     MFVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
@@ -439,12 +459,12 @@ static int launch_tc(const TcPlan* pl, cudaStream_t s) {
   return 0;
 }
 
-template <int BN>
+template <int BN, int CPS>
 static int launch_tc_major(const TcPlan* pl, cudaStream_t s) {
-  if (!pl->a_mn && !pl->b_mn) return launch_tc<BN, false, false>(pl, s);
-  if (!pl->a_mn && pl->b_mn) return launch_tc<BN, false, true>(pl, s);
-  if (pl->a_mn && pl->b_mn) return launch_tc<BN, true, true>(pl, s);
-  return launch_tc<BN, true, false>(pl, s);
+  if (!pl->a_mn && !pl->b_mn) return launch_tc<BN, false, false, CPS>(pl, s);
+  if (!pl->a_mn && pl->b_mn) return launch_tc<BN, false, true, CPS>(pl, s);
+  if (pl->a_mn && pl->b_mn) return launch_tc<BN, true, true, CPS>(pl, s);
+  return launch_tc<BN, true, false, CPS>(pl, s);
 }
 
 int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
@@ -471,8 +491,10 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
       if (t >= kNumSMs) { BN = c; break; }
     }
   }
-  const int n_tiles = (op.N + BN - 1) / BN;
   const int k_blocks = (op.K + BK - 1) / BK;
+  // K <= 256: the tile is a handful of MMAs plus an epilogue -> narrow tiles, three CTAs per SM
+  if (k_blocks <= 4) { BN = 64; pl->cps = 3; }
+  const int n_tiles = (op.N + BN - 1) / BN;
   int splits = 1;
   if (op.epi == kEpiAccum) {
     const long long tiles = static_cast<long long>(op.G) * m_tiles * n_tiles;
@@ -491,7 +513,7 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
   p.aux = static_cast<const __nv_bfloat16*>(op.aux); p.aux_gs = op.aux_gs; p.aux_ld = op.aux_ld;
   p.accumulate_atomic = (op.epi == kEpiAccum && splits > 1) ? 1 : 0;   // single split: plain stores into the zeroed C
   pl->BN = BN;
-  pl->grid = static_cast<int>(std::min<long long>(p.total_work, kNumSMs));
+  pl->grid = static_cast<int>(std::min<long long>(p.total_work, static_cast<long long>(kNumSMs) * pl->cps));
   int rc = encode_operand(&pl->map_a, op.A, op.M, op.K, op.G, op.a_gs, op.a_rs, op.a_cs, BM, &pl->a_mn);
   if (rc == 0) rc = encode_operand(&pl->map_b, op.B, op.N, op.K, op.G, op.b_gs, op.b_rs, op.b_cs, BN, &pl->b_mn);
   if (rc != 0) { delete pl; return rc; }
@@ -501,10 +523,11 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
 
 int gemm_tc_run(const TcPlan* pl, cudaStream_t s) {
   MFVAE_CHECK(pl != nullptr, "tcgen05 GEMM: null plan");
+  if (pl->cps == 3) return launch_tc_major<64, 3>(pl, s);
   switch (pl->BN) {
-    case 64: return launch_tc_major<64>(pl, s);
-    case 128: return launch_tc_major<128>(pl, s);
-    case 256: return launch_tc_major<256>(pl, s);
+    case 64: return launch_tc_major<64, 1>(pl, s);
+    case 128: return launch_tc_major<128, 1>(pl, s);
+    case 256: return launch_tc_major<256, 1>(pl, s);
   }
   MFVAE_FAIL("tcgen05 GEMM: unsupported tile width");
 }

@@ -7,3 +7,4 @@ from . import _lib  # noqa: F401
 from .model import (MAVAE, PackedBatch, Encoder, ActionEncoder, Decoder, reparameterize,  # noqa: F401
                     loss_vae_fn, loss_s_r_vae_fn)
 from .trainer import Trainer, FusedAdam, HostStager, create_dataset, cosine_lr  # noqa: F401
+from .replay_buffer import DeviceRing, MultiAgentCPPRB, JaxFbxBuffer  # noqa: F401

@@ -144,3 +144,59 @@ def test_tcgen05_gemm_against_fp64_reference():
                        text=True, timeout=600, cwd=ROOT)
     sys.stdout.write(r.stdout[-6000:]); sys.stderr.write(r.stderr[-3000:])
     assert r.returncode == 0 and "TC_GEMM_ALL_OK" in r.stdout
+
+
+def test_replay_wrappers_match_reference_contracts(lib):
+    """MultiAgentCPPRB / JaxFbxBuffer over the device ring: key sets and shapes of the reference wrappers
+    (replay_buffer.py:62-81,107-108; jax_buffer.py:45-54,186-188), every sampled row is a stored transition, and the
+    dict feeds create_dataset / the packed batch feeds the train step."""
+    import mfvae_b200 as M
+    spec = O.tiny_spec(3)
+    rng = np.random.default_rng(0)
+
+    class Box:                      # duck-typed gymnasium spaces
+        def __init__(self, n): self.shape = (n,)
+
+    class Env:
+        agents = spec.agents
+        def observation_space(self, a): return Box(spec.obs_dim[a])
+
+    buf = M.MultiAgentCPPRB(Env(), max_size=40, batch_size=16)
+    rows = []
+    for t in range(55):            # wraps the 40-slot ring
+        obs = {a: rng.standard_normal(spec.obs_dim[a]).astype(np.float32) for a in spec.agents}
+        nxt = {a: rng.standard_normal(spec.obs_dim[a]).astype(np.float32) for a in spec.agents}
+        act = {a: int(rng.integers(0, 5)) for a in spec.agents}
+        rew = {a: float(rng.standard_normal()) for a in spec.agents}
+        term = {a: False for a in spec.agents}; trunc = {a: t % 25 == 24 for a in spec.agents}
+        buf.add(obs, nxt, act, rew, term, trunc)
+        rows.append(np.concatenate([obs[a] for a in spec.agents]))
+        if t % 25 == 24:
+            buf.on_episode_end()
+    d = buf.sample()
+    want_keys = {f"{a}_{k}" for a in spec.agents for k in ("observations", "next_observations", "actions", "rewards", "terminals", "truncations")} | {"mask"}
+    assert set(d) == want_keys
+    for a in spec.agents:
+        assert d[f"{a}_observations"].shape == (16, spec.obs_dim[a]) and d[f"{a}_observations"].dtype == np.float32
+        assert d[f"{a}_actions"].shape == (16, 1) and d[f"{a}_rewards"].shape == (16, 1)
+    stored = np.stack(rows[15:])                                        # the 40 newest survive
+    got = np.concatenate([d[f"{a}_observations"] for a in spec.agents], axis=1)
+    for r in got:
+        assert np.any(np.all(np.isclose(stored, r[None, :]), axis=1))
+    idx_state, acts, joint, nxt_t, rew_t = M.create_dataset(d, {a: i for i, a in enumerate(spec.agents)})
+    assert nxt_t.shape == (16, spec.state_dim) and idx_state[spec.agents[0]].shape == (16, 1 + spec.obs_dim[spec.agents[0]])
+    pb = buf.sample_packed()
+    assert pb.obs.shape == (16, spec.state_dim) and pb.obs.is_cuda and pb.rew.shape == (16, 3)
+
+    jb = M.JaxFbxBuffer(max_length=32, min_length=8, batch_size=4)
+    assert jb.can_sample() is None and jb.sample(0) is None            # reference: prints and returns None before init
+    o = {a: rng.standard_normal(spec.obs_dim[a]).astype(np.float32) for a in spec.agents}
+    jb.init_buffer(o, {a: 0.0 for a in o}, {a: 0 for a in o}, o, {a: False for a in o})
+    for t in range(9):
+        jb.add_trans(o, {a: 1.0 for a in o}, {a: 2 for a in o}, o, {a: False for a in o})
+        assert bool(jb.can_sample()) == (t + 1 >= 8)
+    e = jb.sample(123).experience
+    assert set(e) == {f"{a}_{k}" for a in spec.agents for k in ("obs", "act", "next_obs", "rew")} | {"done"}
+    a0 = spec.agents[0]
+    assert e[f"{a0}_obs"].shape == (4, spec.obs_dim[a0], 1) and e[f"{a0}_act"].shape == (4, 1, 1) and e["done"].shape == (4, 1, 1)
+    assert np.allclose(e[f"{a0}_obs"][:, :, 0], o[a0][None, :]) and np.all(e[f"{a0}_act"] == 2)

@@ -151,9 +151,19 @@ template <int BN, int CPS> struct TcCfg {
 // ------------------------------------------------------------------------------------------------
 // epilogue for one 32-column chunk held by one thread (= one output row)
 // ------------------------------------------------------------------------------------------------
+// pack two fp32 into bf16x2 (lo = a, hi = b), optionally clamping at zero in the same instruction
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi, bool relu) {
+  uint32_t d;
+  if (relu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// Every lane of the warp must call this (it shuffles); rows >= M only skip their loads / stores.
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row, int col0, const uint32_t (&v)[32]) {
-  if (row >= p.M) return;
+  const bool row_ok = row < p.M;
   const int ncols = min(32, p.N - col0);
+  const int lane = threadIdx.x & 31;
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -162,23 +172,19 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row
     if (ncols == 32) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const float4 bb = *reinterpret_cast<const float4*>(b + j);
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b + j));
         f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) if (j < ncols) f[j] += b[j];
     }
-    if (p.epi == kEpiBiasRelu) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-    }
-  } else if (p.epi == kEpiReluMask) {
+  } else if (p.epi == kEpiReluMask && row_ok) {
     const __nv_bfloat16* a = p.aux + g * p.aux_gs + static_cast<long long>(row) * p.aux_ld + col0;
     if (ncols == 32) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(a + j);
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(a + j));
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -192,23 +198,44 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row
       for (int j = 0; j < 32; ++j) if (j < ncols && !(__bfloat162float(a[j]) > 0.f)) f[j] = 0.f;
     }
   }
+  const bool relu = (p.epi == kEpiBiasRelu);
   if (p.c_dtype == kBF16) {
-    __nv_bfloat16* c = static_cast<__nv_bfloat16*>(p.C) + g * p.c_gs + static_cast<long long>(row) * p.c_ld + col0;
+    __nv_bfloat16* cbase = static_cast<__nv_bfloat16*>(p.C) + g * p.c_gs + col0;
     if (ncols == 32) {
+      // A lane holds 64 contiguous bytes of its row = two 32-byte sectors, but one store instruction moves 16 bytes per
+      // lane.  Lanes (2i, 2i+1) trade halves so that every instruction writes whole sectors: {A0|A1}, {A2|A3} of the
+      // even row, then {B0|B1}, {B2|B3} of the odd row -- half as many L2 write sectors as 32 row-strided 16-byte pieces.
+      uint32_t pk[16];
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 o;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]), h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(c + j) = o;
+      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1], relu);
+      const bool odd = lane & 1;
+      uint32_t rc[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        rc[i] = __shfl_xor_sync(0xffffffffu, odd ? pk[i] : pk[4 + i], 1);
+        rc[4 + i] = __shfl_xor_sync(0xffffffffu, odd ? pk[8 + i] : pk[12 + i], 1);
       }
-    } else {
+      const int row_e = row & ~1;
+      __nv_bfloat16* ce = cbase + static_cast<long long>(row_e) * p.c_ld + (odd ? 8 : 0);
+      __nv_bfloat16* co = ce + p.c_ld;
+      if (row_e < p.M) {
+        *reinterpret_cast<uint4*>(ce) = odd ? make_uint4(rc[0], rc[1], rc[2], rc[3]) : make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(ce + 16) = odd ? make_uint4(rc[4], rc[5], rc[6], rc[7]) : make_uint4(pk[8], pk[9], pk[10], pk[11]);
+      }
+      if (row_e + 1 < p.M) {
+        *reinterpret_cast<uint4*>(co) = odd ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(rc[0], rc[1], rc[2], rc[3]);
+        *reinterpret_cast<uint4*>(co + 16) = odd ? make_uint4(pk[12], pk[13], pk[14], pk[15]) : make_uint4(rc[4], rc[5], rc[6], rc[7]);
+      }
+    } else if (row_ok) {
+      __nv_bfloat16* c = cbase + static_cast<long long>(row) * p.c_ld;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < ncols) c[j] = __float2bfloat16_rn(f[j]);
+      for (int j = 0; j < 32; ++j) if (j < ncols) c[j] = __float2bfloat16_rn(relu ? fmaxf(f[j], 0.f) : f[j]);
     }
-  } else {
+  } else if (row_ok) {
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
     float* c = static_cast<float*>(p.C) + g * p.c_gs + static_cast<long long>(row) * p.c_ld + col0;
     if (p.accumulate_atomic) {
       if (ncols == 32) {      // 128-bit vector reductions: 4x fewer L2 atomic operations than scalar red.f32
@@ -250,6 +277,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // programmatic dependent launch: let the next kernel of the stream begin its own prologue as CTAs of this one retire
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a); prefetch_tmap(&map_b);
@@ -262,6 +291,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of the previous kernel;
+  // from here on global memory written by it is read
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const long long tiles_per_split = static_cast<long long>(p.m_tiles) * p.n_tiles;
 
@@ -454,7 +486,13 @@ static int launch_tc(const TcPlan* pl, cudaStream_t s) {
     MFVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  kern<<<pl->grid, kTcThreads, Cfg::kSmemBytes, s>>>(pl->map_a, pl->map_b, pl->prm);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(pl->grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  MFVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->map_a, pl->map_b, pl->prm));
   MFVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -530,14 +530,21 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
     }
   }
   const int k_blocks = (op.K + BK - 1) / BK;
-  // K <= 256: the tile is a handful of MMAs plus an epilogue -> narrow tiles, three CTAs per SM
-  if (k_blocks <= 4) { BN = 64; pl->cps = 3; }
+  // Narrow tiles, three co-resident CTAs per SM (75 KB smem, 128 TMEM columns each) when
+  //  * K <= 256: the tile is a handful of MMAs plus an epilogue, latency hiding comes from the neighbours; or
+  //  * wide tiles cannot give every SM one tile anyway (the small layers): a CTA of this shape leaves room for the
+  //    kernels of the other backward chain (side stream) on the same SM, and 3 x 72 KB of operands in flight per SM
+  //    covers the L2 latency-bandwidth product as well as one deep ring does.
+  {
+    const long long wide_tiles = static_cast<long long>(op.G) * m_tiles * ((op.N + 255) / 256);
+    if (k_blocks <= 4 || wide_tiles < kNumSMs) { BN = 64; pl->cps = 3; }
+  }
   const int n_tiles = (op.N + BN - 1) / BN;
   int splits = 1;
   if (op.epi == kEpiAccum) {
     const long long tiles = static_cast<long long>(op.G) * m_tiles * n_tiles;
     long long want = op.split_k > 1 ? op.split_k : 1;
-    want = std::max<long long>(want, (kNumSMs + tiles - 1) / tiles);
+    want = std::max<long long>(want, (static_cast<long long>(kNumSMs) * pl->cps + tiles - 1) / tiles);
     splits = static_cast<int>(std::max<long long>(1, std::min<long long>(want, std::max(1, k_blocks / 4))));
   }
   const int kb_per_split = (k_blocks + splits - 1) / splits;

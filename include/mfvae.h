@@ -136,6 +136,9 @@ int mfvae_backward(MfvaeHandle h, const MfvaeBatch* b, void* stream);
 int mfvae_backward_ext(MfvaeHandle h, const MfvaeBatch* b, const float* d_g_recon_s, int64_t ld_s,
                        const float* d_g_recon_r, int64_t ld_r, const float* d_g_latent, void* stream);
 int mfvae_adam_step(MfvaeHandle h, float lr, float beta1, float beta2, float eps, int64_t t, void* stream);
+/* same update; the decoder block runs on an internal stream as soon as its gradient buckets are final (overlapping the
+ * encoder half of backward).  Only valid when no collective has to run between backward and the update (1 GPU). */
+int mfvae_adam_step_overlapped(MfvaeHandle h, float lr, float beta1, float beta2, float eps, int64_t t, void* stream);
 /* forward + loss + backward in one call (no optimizer; the host all-reduces gradients in between) */
 int mfvae_fwd_bwd(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* stream);
 

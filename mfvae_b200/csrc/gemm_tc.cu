@@ -532,13 +532,10 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
   const int k_blocks = (op.K + BK - 1) / BK;
   // Narrow tiles, three co-resident CTAs per SM (75 KB smem, 128 TMEM columns each) when
   //  * K <= 256: the tile is a handful of MMAs plus an epilogue, latency hiding comes from the neighbours; or
-  //  * wide tiles cannot give every SM one tile anyway (the small layers): a CTA of this shape leaves room for the
+  //  * 128-wide tiles cannot give every SM one tile anyway (the small layers): a CTA of this shape leaves room for the
   //    kernels of the other backward chain (side stream) on the same SM, and 3 x 72 KB of operands in flight per SM
   //    covers the L2 latency-bandwidth product as well as one deep ring does.
-  {
-    const long long wide_tiles = static_cast<long long>(op.G) * m_tiles * ((op.N + 255) / 256);
-    if (k_blocks <= 4 || wide_tiles < kNumSMs) { BN = 64; pl->cps = 3; }
-  }
+  if (k_blocks <= 4 || BN == 64) { BN = 64; pl->cps = 3; }     // BN == 64 here: not even 128-wide tiles reach 148
   const int n_tiles = (op.N + BN - 1) / BN;
   int splits = 1;
   if (op.epi == kEpiAccum) {
@@ -578,5 +575,6 @@ int gemm_tc_run(const TcPlan* pl, cudaStream_t s) {
 }
 
 void gemm_tc_free(TcPlan* p) { delete p; }
+bool gemm_tc_overwrites(const TcPlan* p) { return p && p->prm.accumulate_atomic == 0; }
 
 }  // namespace mfvae

@@ -103,5 +103,6 @@ struct TcPlan;
 int gemm_tc_plan(const GemmOp& op, TcPlan** out);       // validates alignment, encodes CUtensorMaps
 int gemm_tc_run(const TcPlan* p, cudaStream_t s);
 void gemm_tc_free(TcPlan* p);
+bool gemm_tc_overwrites(const TcPlan* p);               // true: C is fully written by plain stores (no pre-zeroing needed)
 
 }  // namespace mfvae

@@ -74,6 +74,8 @@ struct MfvaeHandle_ {
   cudaStream_t side = nullptr;
   std::vector<cudaEvent_t> fork_ev;
   cudaEvent_t join_ev = nullptr;
+  cudaStream_t opt_stream = nullptr;         // overlapped Adam
+  cudaEvent_t opt_ev = nullptr, dec_read_ev = nullptr;
 
   // optional per-GEMM event timing (bench.py roofline)
   bool profiling = false;
@@ -442,8 +444,20 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
     ++ev_i;
     return 0;
   };
-  // optimizer.zero_grad(): split-K wgrads and bias column sums accumulate with fp32 atomics
-  MFVAE_CUDA(cudaMemsetAsync(G, 0, static_cast<size_t>(h->arena_elems) * sizeof(float), s));
+  // optimizer.zero_grad(): split-K wgrads and bias column sums accumulate with fp32 atomics.  The two largest weight
+  // gradients (decoder layer 0, state output layer) are written by single-split wgrads with plain stores and are
+  // skipped (they are 2/3 of the arena).
+  {
+    int64_t skip[2][2]; int ns = 0;
+    if (h->use_tc && gemm_tc_overwrites(h->tc[h->g_dec_wg[0]])) { skip[ns][0] = h->decW[0].off; skip[ns][1] = h->decB[0].off; ++ns; }
+    if (h->use_tc && gemm_tc_overwrites(h->tc[h->g_sout_wg])) { skip[ns][0] = h->sOutW.off; skip[ns][1] = h->sOutB.off; ++ns; }
+    int64_t cur = 0;
+    for (int i = 0; i <= ns; ++i) {
+      const int64_t end = (i < ns) ? skip[i][0] : h->arena_elems;
+      if (end > cur) MFVAE_CUDA(cudaMemsetAsync(G + cur, 0, static_cast<size_t>(end - cur) * sizeof(float), s));
+      if (i < ns) cur = skip[i][1];
+    }
+  }
   MFVAE_TRY(fork());                                            // D(recon_s), D(recon_r) and the zeroed arena are ready
   // output layers + reward_linear
   MFVAE_TRY(run_gemm(h, h->g_sout_wg, w));
@@ -467,6 +481,7 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
   }
   if (nh == 1) MFVAE_CUDA(cudaEventRecord(h->buckets[1].ev, w));
   MFVAE_CUDA(cudaEventRecord(h->buckets[2].ev, w));
+  if (h->dec_read_ev) MFVAE_CUDA(cudaEventRecord(h->dec_read_ev, s));   // last reader of the decoder weights (dgrad layer 0) is queued
   // action tables (model.py:121: unregistered; gradients still flow)
   MFVAE_TRY(launch_act_table_grad(ws + h->GZIN.off, dt, h->GZIN.ld, A * h->L, b->d_act, A, h->d_meta + 2 * A, A, h->C, h->B,
                                   G + h->actT.off, static_cast<int64_t>(h->nact_max) * h->C, s));
@@ -547,6 +562,9 @@ int mfvae_create(const MfvaeConfig* cfg, int device, MfvaeHandle* out) {
     h->fork_ev.push_back(e);
   }
   cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming);
+  if (cudaStreamCreateWithFlags(&h->opt_stream, cudaStreamNonBlocking) != cudaSuccess) h->opt_stream = nullptr;
+  cudaEventCreateWithFlags(&h->opt_ev, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->dec_read_ev, cudaEventDisableTiming);
   std::vector<int32_t> meta;
   meta.insert(meta.end(), h->obs_off.begin(), h->obs_off.end());
   meta.insert(meta.end(), h->obs_dim.begin(), h->obs_dim.end());
@@ -567,6 +585,9 @@ int mfvae_destroy(MfvaeHandle h) {
   for (auto e : h->fork_ev) if (e) cudaEventDestroy(e);
   if (h->join_ev) cudaEventDestroy(h->join_ev);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->opt_ev) cudaEventDestroy(h->opt_ev);
+  if (h->dec_read_ev) cudaEventDestroy(h->dec_read_ev);
+  if (h->opt_stream) cudaStreamDestroy(h->opt_stream);
   if (h->d_meta) cudaFree(h->d_meta);
   delete h;
   return 0;
@@ -663,6 +684,29 @@ int mfvae_adam_step(MfvaeHandle h, float lr, float beta1, float beta2, float eps
   return launch_adam(h->ar.d_param, h->ar.d_grad, h->ar.d_m, h->ar.d_v,
                      static_cast<__nv_bfloat16*>(h->ar.d_shadow_bf16), h->optimized_elems, lr, beta1, beta2, eps, t,
                      static_cast<cudaStream_t>(stream));
+}
+
+// Adam for the decoder block of the arena on a third stream as soon as its gradient buckets are final, so that the
+// 28 B/parameter sweep overlaps the encoder half of backward still running on the caller's stream; the remaining
+// ranges (idx_emb, and the encoders when they are optimised) follow on the caller's stream, which then joins.
+int mfvae_adam_step_overlapped(MfvaeHandle h, float lr, float beta1, float beta2, float eps, int64_t t, void* stream) {
+  MFVAE_CHECK(h && h->ar.d_param, "arenas are not bound");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!h->opt_stream || h->profiling) return mfvae_adam_step(h, lr, beta1, beta2, eps, t, stream);
+  __nv_bfloat16* sh = static_cast<__nv_bfloat16*>(h->ar.d_shadow_bf16);
+  auto range = [&](int64_t b, int64_t e, cudaStream_t st) -> int {
+    if (e <= b) return 0;
+    return launch_adam(h->ar.d_param + b, h->ar.d_grad + b, h->ar.d_m + b, h->ar.d_v + b, sh ? sh + b : nullptr, e - b,
+                       lr, beta1, beta2, eps, t, st);
+  };
+  for (int i = 0; i < 3; ++i) MFVAE_CUDA(cudaStreamWaitEvent(h->opt_stream, h->buckets[i].ev, 0));
+  MFVAE_CUDA(cudaStreamWaitEvent(h->opt_stream, h->dec_read_ev, 0));    // the dgrad chain has finished reading the decoder weights
+  MFVAE_TRY(range(h->reg2_begin, h->enc_begin, h->opt_stream));
+  MFVAE_CUDA(cudaEventRecord(h->opt_ev, h->opt_stream));
+  MFVAE_TRY(range(0, h->reg2_begin, s));
+  if (h->optimized_elems > h->enc_begin) MFVAE_TRY(range(h->enc_begin, h->optimized_elems, s));
+  MFVAE_CUDA(cudaStreamWaitEvent(s, h->opt_ev, 0));
+  return 0;
 }
 
 uint64_t mfvae_launch_count(void) { return g_launch_count; }

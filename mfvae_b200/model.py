@@ -563,11 +563,14 @@ class MAVAE(nn.Module):
             w.wait()
         main.wait_stream(self._comm_stream)
 
-    def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8):
-        """Fused Adam over the registered (optimised) prefix of the arena; also refreshes the bf16 shadow."""
+    def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, overlapped=False):
+        """Fused Adam over the registered (optimised) prefix of the arena; also refreshes the bf16 shadow.
+        ``overlapped`` (single GPU, called right after backward): the decoder block is updated on an internal stream
+        as soon as its gradients are final, concurrently with the encoder half of backward."""
         self._require_gpu()
         self._adam_t += 1
-        L.check(L.lib().mfvae_adam_step(self._h, float(lr), float(betas[0]), float(betas[1]), float(eps), self._adam_t, self._stream()))
+        fn = L.lib().mfvae_adam_step_overlapped if overlapped else L.lib().mfvae_adam_step
+        L.check(fn(self._h, float(lr), float(betas[0]), float(betas[1]), float(eps), self._adam_t, self._stream()))
 
     def train_step(self, pb: PackedBatch, lr: float, betas=(0.9, 0.999), eps=1e-8):
         """Fast path: forward + fused ELBO + backward (+ all-reduce) + Adam, no autograd graph.
@@ -584,5 +587,5 @@ class MAVAE(nn.Module):
         self.philox_step += 1
         if self.data_parallel:
             self._allreduce_grads()
-        self.adam_step(lr, betas, eps)
+        self.adam_step(lr, betas, eps, overlapped=not self.data_parallel)
         return self._losses

@@ -32,6 +32,9 @@ enum { MFVAE_PREC_FP32 = 0, MFVAE_PREC_BF16 = 1 };
 /* GEMM engines.  AUTO = tcgen05 for bf16, SIMT FFMA for fp32.  SIMT with bf16 is a debugging aid that
  * runs the same data flow without tensor cores; it is NOT a fallback: nothing selects it implicitly. */
 enum { MFVAE_ENGINE_AUTO = 0, MFVAE_ENGINE_SIMT = 1, MFVAE_ENGINE_TCGEN05 = 2 };
+/* AUTO = every fused kernel whose shape constraints hold (the per-agent encoder chain as one kernel per direction);
+ * NONE = one kernel per layer.  Both compute the same values with the same rounding points. */
+enum { MFVAE_FUSE_AUTO = 0, MFVAE_FUSE_NONE = 1 };
 enum { MFVAE_LOSS_DEFAULT = 0, MFVAE_LOSS_HUBER = 1, MFVAE_LOSS_MSE = 2, MFVAE_LOSS_JOINT_MSE = 3 };
 
 typedef struct MfvaeConfig {
@@ -52,6 +55,7 @@ typedef struct MfvaeConfig {
   int32_t engine;                        /* MFVAE_ENGINE_*                                   */
   int32_t optimize_encoders;             /* 0 = reference semantics: encoders / action tables get
                                             gradients but no Adam update (model.py:112,114)  */
+  int32_t fusion;                        /* MFVAE_FUSE_*: cross-layer kernel fusion (tcgen05 engine only)  */
 } MfvaeConfig;
 
 /* One tensor of the parameter arena.  Offsets are in ELEMENTS and identical for the fp32 master,

@@ -12,6 +12,7 @@ MAX_HIDDEN = 8
 
 PREC_FP32, PREC_BF16 = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+FUSE_AUTO, FUSE_NONE = 0, 1
 LOSS_DEFAULT, LOSS_HUBER, LOSS_MSE, LOSS_JOINT_MSE = 0, 1, 2, 3
 (T_IDX_EMB, T_ENC_W, T_ENC_B, T_ACT_TABLE, T_SDEC_W, T_SDEC_B, T_RDEC_W, T_RDEC_B, T_RLIN_W, T_RLIN_B) = range(10)
 
@@ -22,7 +23,8 @@ class MfvaeConfig(C.Structure):
                 ("n_dec_hidden", C.c_int32), ("dec_hidden", C.c_int32 * MAX_HIDDEN),
                 ("obs_dim", C.POINTER(C.c_int32)), ("n_act", C.POINTER(C.c_int32)),
                 ("kl_weight", C.c_float), ("r_weight", C.c_float), ("huber", C.c_int32),
-                ("precision", C.c_int32), ("engine", C.c_int32), ("optimize_encoders", C.c_int32)]
+                ("precision", C.c_int32), ("engine", C.c_int32), ("optimize_encoders", C.c_int32),
+                ("fusion", C.c_int32)]
 
 
 class MfvaeTensorInfo(C.Structure):

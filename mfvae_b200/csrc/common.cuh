@@ -129,4 +129,32 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
+constexpr int kMaxPartials = 2048;          // scratch[0..2047] partials, scratch[4095] ticket
+constexpr int kTicketSlot = 4095;
+
+
+// Sum per-CTA partials in a fixed order once every CTA has published; the last CTA to take a ticket
+// does it, then re-arms the ticket for the next launch.
+__device__ __forceinline__ void finish_scalar(float block_total, float* scratch, float scale, float* out,
+                                              float* red) {
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+    scratch[blockIdx.x] = block_total;
+    __threadfence();
+    unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(scratch + kTicketSlot), 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float v = 0.f;
+    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += blockDim.x) v += __ldcg(scratch + i);
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) {
+      out[0] = v * scale;
+      *reinterpret_cast<unsigned int*>(scratch + kTicketSlot) = 0u;
+    }
+  }
+}
+
 }  // namespace mfvae

@@ -17,39 +17,12 @@
 namespace mfvae {
 
 constexpr int kThreads = 256;
-constexpr int kMaxPartials = 2048;          // scratch[0..2047] partials, scratch[4095] ticket
-constexpr int kTicketSlot = 4095;
-
 static inline int grid_for(int64_t work_items, int per_sm = 8) {
   int64_t blocks = (work_items + kThreads - 1) / kThreads;
   int64_t cap = static_cast<int64_t>(kNumSMs) * per_sm;     // multiple of the SM count
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return static_cast<int>(blocks);
-}
-
-// Sum per-CTA partials in a fixed order once every CTA has published; the last CTA to take a ticket
-// does it, then re-arms the ticket for the next launch.
-__device__ __forceinline__ void finish_scalar(float block_total, float* scratch, float scale, float* out,
-                                              float* red) {
-  __shared__ bool is_last;
-  if (threadIdx.x == 0) {
-    scratch[blockIdx.x] = block_total;
-    __threadfence();
-    unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(scratch + kTicketSlot), 1u);
-    is_last = (ticket == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    float v = 0.f;
-    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += blockDim.x) v += __ldcg(scratch + i);
-    v = block_sum(v, red);
-    if (threadIdx.x == 0) {
-      out[0] = v * scale;
-      *reinterpret_cast<unsigned int*>(scratch + kTicketSlot) = 0u;
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -120,7 +93,7 @@ __global__ void __launch_bounds__(kThreads) act_embed_kernel(StageArgs p) {
   }
 }
 
-int launch_stage(const StageArgs& a, cudaStream_t s) {
+int launch_stage(const StageArgs& a, cudaStream_t s, bool do_x0, bool do_act) {
   MFVAE_CHECK(a.x0_ld % 4 == 0 && a.C % 4 == 0 && a.zin_ld % 4 == 0, "stage: widths must be multiples of 4");
   const int64_t t0 = static_cast<int64_t>(a.A) * a.B * (a.x0_ld / 4);
   const int64_t t1 = static_cast<int64_t>(a.A) * a.B * (a.C / 4);
@@ -129,15 +102,16 @@ int launch_stage(const StageArgs& a, cudaStream_t s) {
   const int rpp = kThreads / (nvec <= 32 ? 32 : (nvec <= 64 ? 64 : 128));
   const int chunks = std::max(1, std::min((a.B + rpp * 4 - 1) / (rpp * 4), std::max(1, kNumSMs * 16 / a.A)));
   dim3 sgrid(chunks, a.A);
-  if (a.dtype == kBF16) {
-    stage_kernel<__nv_bfloat16><<<sgrid, kThreads, 0, s>>>(a);
-    act_embed_kernel<__nv_bfloat16><<<grid_for(t1), kThreads, 0, s>>>(a);
-  } else {
-    stage_kernel<float><<<sgrid, kThreads, 0, s>>>(a);
-    act_embed_kernel<float><<<grid_for(t1), kThreads, 0, s>>>(a);
+  if (do_x0) {
+    if (a.dtype == kBF16) stage_kernel<__nv_bfloat16><<<sgrid, kThreads, 0, s>>>(a);
+    else                  stage_kernel<float><<<sgrid, kThreads, 0, s>>>(a);
+    MFVAE_LAUNCH_CHECK();
   }
-  ++g_launch_count;
-  MFVAE_LAUNCH_CHECK();
+  if (do_act) {
+    if (a.dtype == kBF16) act_embed_kernel<__nv_bfloat16><<<grid_for(t1), kThreads, 0, s>>>(a);
+    else                  act_embed_kernel<float><<<grid_for(t1), kThreads, 0, s>>>(a);
+    MFVAE_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+struct CUtensorMap_st;            // CUtensorMap of <cuda.h>
+
 namespace mfvae {
 
 enum DType { kF32 = 0, kBF16 = 1 };
@@ -20,7 +22,8 @@ struct StageArgs {
   int A, I, L, C, B;
   int dtype;
 };
-int launch_stage(const StageArgs& a, cudaStream_t s);
+// do_x0: encoder inputs X0; do_act: action-embedding half of the decoder input
+int launch_stage(const StageArgs& a, cudaStream_t s, bool do_x0 = true, bool do_act = true);
 
 struct ReparamArgs {
   const float* mu; const float* lv;      // element (b,a,j) at p + a*lat_as + b*lat_bs + j
@@ -104,5 +107,33 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out);       // validates alignment, 
 int gemm_tc_run(const TcPlan* p, cudaStream_t s);
 void gemm_tc_free(TcPlan* p);
 bool gemm_tc_overwrites(const TcPlan* p);               // true: C is fully written by plain stores (no pre-zeroing needed)
+
+// ---- fused per-agent encoder (enc_fused.cu) ---------------------------------------------------
+constexpr int kEncMaxL = 4;
+struct EncFusedDesc {                          // everything that is fixed once arenas + workspace are bound
+  int A = 0, B = 0, nl = 0, I = 0, L = 0, K0p = 0;
+  int N[kEncMaxL] = {0, 0, 0, 0};              // output width of layer l (last = 2L)
+  const void* W[kEncMaxL] = {};                // bf16 [A][N_l][K_l]
+  const float* bias[kEncMaxL] = {};            // fp32 [A][N_l]
+  void* X[kEncMaxL] = {};                      // bf16 input of layer l, [A][B][x_ld]: X0, XE_0, ...
+  int64_t x_ld[kEncMaxL] = {}, x_gs[kEncMaxL] = {};
+  const float* idx_emb = nullptr; const int32_t* obs_off = nullptr; const int32_t* obs_dim = nullptr;
+  float* lat = nullptr; int64_t lat_gs = 0, lat_ld = 0;
+  void* zin = nullptr; int64_t zin_ld = 0;
+};
+struct EncFwdBatch {
+  const float* obs; int64_t obs_ld; const float* idx; int idx_ld;
+  const float* eps; int64_t eps_ld; uint64_t seed, step; int64_t sample0;
+  float kl_scale; float* kl_out; float* scratch;
+};
+struct EncFusedPlan;
+bool enc_fused_applicable(const EncFusedDesc& d);
+int enc_fused_plan(const EncFusedDesc& d, EncFusedPlan** out);
+void enc_fused_free(EncFusedPlan* p);
+int enc_fused_forward(EncFusedPlan* p, const EncFwdBatch& b, cudaStream_t s);
+
+// shared tensor-map encoder (gemm_tc.cu)
+int encode_tmap_bf16_3d(::CUtensorMap_st* map, const void* base, int64_t inner, int64_t outer, int64_t G, int64_t ld, int64_t gs,
+                        int box_inner, int box_outer);
 
 }  // namespace mfvae

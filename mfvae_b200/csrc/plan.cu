@@ -66,6 +66,7 @@ struct MfvaeHandle_ {
   // GEMM ops
   std::vector<GemmOp> gemms;
   std::vector<TcPlan*> tc;
+  EncFusedPlan* enc_fused = nullptr;         // fused per-agent encoder chain (enc_fused.cu), when its shape constraints hold
   std::vector<int> g_enc_fwd, g_enc_wg, g_enc_dg, g_dec_fwd, g_dec_wg, g_dec_dg;
   int g_sout_fwd = -1, g_rout_fwd = -1, g_rl_fwd = -1;
   int g_sout_wg = -1, g_sout_dg = -1, g_rout_wg = -1, g_rout_dg = -1, g_rl_wg = -1, g_rl_dg = -1;
@@ -218,6 +219,7 @@ static int64_t layout_workspace(MfvaeHandle_* h, int B) {
 
 static void free_plans(MfvaeHandle_* h) {
   for (TcPlan* p : h->tc) if (p) gemm_tc_free(p);
+  if (h->enc_fused) { enc_fused_free(h->enc_fused); h->enc_fused = nullptr; }
   h->tc.clear(); h->gemms.clear();
   h->g_enc_fwd.clear(); h->g_enc_wg.clear(); h->g_enc_dg.clear();
   h->g_dec_fwd.clear(); h->g_dec_wg.clear(); h->g_dec_dg.clear();
@@ -338,6 +340,22 @@ static int build_ops(MfvaeHandle_* h) {
   if (h->use_tc) {
     for (size_t i = 0; i < h->gemms.size(); ++i) MFVAE_TRY(gemm_tc_plan(h->gemms[i], &h->tc[i]));
   }
+  // ---- fused encoder chain ----
+  if (h->use_tc && h->cfg.fusion == MFVAE_FUSE_AUTO && h->ne <= kEncMaxL) {
+    EncFusedDesc d;
+    d.A = A; d.B = B; d.nl = h->ne; d.I = h->I; d.L = h->L; d.K0p = h->K0p;
+    for (int l = 0; l < h->ne; ++l) {
+      const MfvaeHandle_::Buf& in = (l == 0) ? h->X0 : h->XE[l - 1];
+      d.N[l] = h->encN[l];
+      d.W[l] = wptr(h->encW[l].off);
+      d.bias[l] = P + h->encB[l].off;
+      d.X[l] = buf(in); d.x_ld[l] = in.ld; d.x_gs[l] = in.gs;
+    }
+    d.idx_emb = P + h->idx_emb.off; d.obs_off = h->d_meta; d.obs_dim = h->d_meta + A;
+    d.lat = reinterpret_cast<float*>(ws + h->LAT.off); d.lat_gs = h->LAT.gs; d.lat_ld = h->LAT.ld;
+    d.zin = ws + h->ZIN.off; d.zin_ld = h->ZIN.ld;
+    if (enc_fused_applicable(d)) MFVAE_TRY(enc_fused_plan(d, &h->enc_fused));
+  }
   return 0;
 }
 
@@ -362,6 +380,14 @@ static int check_ready(MfvaeHandle_* h, const MfvaeBatch* b) {
 static float* losses_ptr(MfvaeHandle_* h) { return reinterpret_cast<float*>(h->ws + h->off_losses); }
 static float* scratch_ptr(MfvaeHandle_* h, int i) { return reinterpret_cast<float*>(h->ws + h->off_scratch) + 4096 * i; }
 
+static int do_forward_decoders(MfvaeHandle_* h, cudaStream_t s) {
+  for (int l = 0; l < h->cfg.n_dec_hidden; ++l) MFVAE_TRY(run_gemm(h, h->g_dec_fwd[l], s));
+  MFVAE_TRY(run_gemm(h, h->g_sout_fwd, s));
+  MFVAE_TRY(run_gemm(h, h->g_rout_fwd, s));
+  MFVAE_TRY(run_gemm(h, h->g_rl_fwd, s));
+  return 0;
+}
+
 static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, cudaStream_t s) {
   MFVAE_TRY(check_ready(h, b));
   StageArgs st{};
@@ -372,10 +398,25 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
   st.x0 = h->ws + h->X0.off; st.x0_ld = static_cast<int>(h->X0.ld); st.x0_gs = h->X0.gs;
   st.zin = h->ws + h->ZIN.off; st.zin_ld = static_cast<int>(h->ZIN.ld);
   st.A = h->A; st.I = h->I; st.L = h->L; st.C = h->C; st.B = h->B; st.dtype = h->dtype;
+  const float* lat = reinterpret_cast<const float*>(h->ws + h->LAT.off);
+  if (out) {
+    out->d_recon_s = reinterpret_cast<const float*>(h->ws + h->RS.off); out->recon_s_ld = static_cast<int32_t>(h->RS.ld);
+    out->d_recon_r = reinterpret_cast<const float*>(h->ws + h->RR.off); out->recon_r_ld = static_cast<int32_t>(h->RR.ld);
+    out->d_latent = lat; out->d_losses = losses_ptr(h);
+  }
+  if (h->enc_fused) {
+    // staging of X0, the four encoder layers, reparameterisation and KL: one kernel (enc_fused.cu)
+    MFVAE_TRY(launch_stage(st, s, false, true));
+    EncFwdBatch eb{};
+    eb.obs = b->d_obs; eb.obs_ld = h->S; eb.idx = b->d_idx; eb.idx_ld = h->A;
+    eb.eps = b->d_eps; eb.eps_ld = static_cast<int64_t>(h->A) * h->L; eb.seed = b->seed; eb.step = b->step; eb.sample0 = b->sample0;
+    eb.kl_scale = 1.0f / static_cast<float>(b->batch_global); eb.kl_out = losses_ptr(h) + 3; eb.scratch = scratch_ptr(h, 0);
+    MFVAE_TRY(enc_fused_forward(h->enc_fused, eb, s));
+    return do_forward_decoders(h, s);
+  }
   MFVAE_TRY(launch_stage(st, s));
   for (int l = 0; l < h->ne; ++l) MFVAE_TRY(run_gemm(h, h->g_enc_fwd[l], s));
   ReparamArgs rp{};
-  const float* lat = reinterpret_cast<const float*>(h->ws + h->LAT.off);
   rp.mu = lat; rp.lv = lat + h->L; rp.lat_as = h->LAT.gs; rp.lat_bs = h->LAT.ld;
   rp.eps = b->d_eps; rp.eps_ld = static_cast<int64_t>(h->A) * h->L;
   rp.z = h->ws + h->ZIN.off; rp.z_ld = h->ZIN.ld; rp.z_dtype = h->dtype;
@@ -383,16 +424,7 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
   rp.kl_scale = 1.0f / static_cast<float>(b->batch_global);
   rp.kl_out = losses_ptr(h) + 3; rp.scratch = scratch_ptr(h, 0);
   MFVAE_TRY(launch_reparam_kl_fwd(rp, s));
-  for (int l = 0; l < h->cfg.n_dec_hidden; ++l) MFVAE_TRY(run_gemm(h, h->g_dec_fwd[l], s));
-  MFVAE_TRY(run_gemm(h, h->g_sout_fwd, s));
-  MFVAE_TRY(run_gemm(h, h->g_rout_fwd, s));
-  MFVAE_TRY(run_gemm(h, h->g_rl_fwd, s));
-  if (out) {
-    out->d_recon_s = reinterpret_cast<const float*>(h->ws + h->RS.off); out->recon_s_ld = static_cast<int32_t>(h->RS.ld);
-    out->d_recon_r = reinterpret_cast<const float*>(h->ws + h->RR.off); out->recon_r_ld = static_cast<int32_t>(h->RR.ld);
-    out->d_latent = lat; out->d_losses = losses_ptr(h);
-  }
-  return 0;
+  return do_forward_decoders(h, s);
 }
 
 static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStream_t s) {

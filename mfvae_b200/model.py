@@ -196,7 +196,8 @@ class MAVAE(nn.Module):
                  agents: list, obs_dim: dict, action_dim: dict, device: str, *,
                  precision: str = "bf16", engine: str = "auto", enc_hidden: Optional[Sequence[int]] = None,
                  dec_hidden: Optional[Sequence[int]] = None, optimize_encoders: bool = False,
-                 include_dead_decoder: bool = True, seed: int = 0x5EED, huber: bool = True):
+                 include_dead_decoder: bool = True, seed: int = 0x5EED, huber: bool = True,
+                 fusion: str = "auto"):
         super().__init__()
         if not descrete_act:
             raise NotImplementedError("continuous-action ActionEncoder path (model.py:123,148) is not built yet")
@@ -235,6 +236,7 @@ class MAVAE(nn.Module):
         cfg.precision = {"fp32": L.PREC_FP32, "bf16": L.PREC_BF16}[precision]
         cfg.engine = {"auto": L.ENGINE_AUTO, "simt": L.ENGINE_SIMT, "tcgen05": L.ENGINE_TCGEN05}[engine]
         cfg.optimize_encoders = int(self.optimize_encoders)
+        cfg.fusion = {"auto": L.FUSE_AUTO, "none": L.FUSE_NONE}[fusion]
         self._cfg = cfg
         lib = L.lib()
         self._h = C.c_void_p()

@@ -32,9 +32,11 @@ enum { MFVAE_PREC_FP32 = 0, MFVAE_PREC_BF16 = 1 };
 /* GEMM engines.  AUTO = tcgen05 for bf16, SIMT FFMA for fp32.  SIMT with bf16 is a debugging aid that
  * runs the same data flow without tensor cores; it is NOT a fallback: nothing selects it implicitly. */
 enum { MFVAE_ENGINE_AUTO = 0, MFVAE_ENGINE_SIMT = 1, MFVAE_ENGINE_TCGEN05 = 2 };
-/* AUTO = every fused kernel whose shape constraints hold (the per-agent encoder chain as one kernel per direction);
- * NONE = one kernel per layer.  Both compute the same values with the same rounding points. */
-enum { MFVAE_FUSE_AUTO = 0, MFVAE_FUSE_NONE = 1 };
+/* NONE = one kernel per layer.  ENCODER = staging + the per-agent encoder chain + reparameterisation + KL as ONE
+ * persistent tcgen05 kernel (enc_fused.cu; falls back to per-layer kernels when its shape constraints do not hold).
+ * AUTO = the variant that measured fastest on B200 (today: NONE).  All variants compute the
+ * same values with the same rounding points. */
+enum { MFVAE_FUSE_AUTO = 0, MFVAE_FUSE_NONE = 1, MFVAE_FUSE_ENCODER = 2 };
 enum { MFVAE_LOSS_DEFAULT = 0, MFVAE_LOSS_HUBER = 1, MFVAE_LOSS_MSE = 2, MFVAE_LOSS_JOINT_MSE = 3 };
 
 typedef struct MfvaeConfig {

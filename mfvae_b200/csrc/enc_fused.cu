@@ -35,12 +35,15 @@ constexpr size_t kEncSmemLimit = 227 * 1024 - 1024;   // dynamic + static shared
 struct EncFwdParams {
   int A, B, tiles, total_units, nl;
   int N[kEncMaxL], kboxes[kEncMaxL], ksteps[kEncMaxL], tmem_col[kEncMaxL];
+  int in_box[kEncMaxL], wait_store[kEncMaxL];   // first activation box of layer l's input; 1: its TMA store must drain before the epilogue
   uint32_t w_off[kEncMaxL], w_bytes;           // weight offsets inside the weight region / its size
+  int bias_n;                                  // sum of N_l (= TMEM columns in use): bias l lives at [tmem_col[l], +N_l)
   const float* bias[kEncMaxL];                 // [A][N_l] fp32
   const float* obs; long long obs_ld;
   const float* idx; int idx_ld;                // optional explicit agent-index column [B][A]
   const float* idx_emb; int I;
   const int32_t* obs_off; const int32_t* obs_dim;
+  __nv_bfloat16* xout[kEncMaxL]; long long xout_gs[kEncMaxL], xout_ld[kEncMaxL]; int xout_w[kEncMaxL];   // input of layer l in HBM
   float* lat; long long lat_gs, lat_ld;
   __nv_bfloat16* zin; long long zin_ld;
   const float* eps; long long eps_ld;
@@ -49,6 +52,13 @@ struct EncFwdParams {
   float kl_scale; float* kl_out; float* scratch;
 };
 struct alignas(64) EncMaps { CUtensorMap w[kEncMaxL]; CUtensorMap x[kEncMaxL]; };
+
+enum { kStageNone = 0, kStageEmb, kStageEmbIdx, kStageVec, kStageScalar, kStageZero };
+struct StageLane {                             // one lane's role in building X0 rows of the unit being staged
+  int kind, a, b0, nvalid, off;
+  const float* src0;
+  uint4 emb;
+};
 
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack_bf16x2(f[0], f[1], false), pack_bf16x2(f[2], f[3], false), pack_bf16x2(f[4], f[5], false),
@@ -66,12 +76,15 @@ enc_fwd_kernel(const __grid_constant__ EncMaps maps, const EncFwdParams p) {
   uint64_t* act_ready = bars;
   uint64_t* mma_done = bars + kEncMaxL;
   uint64_t* w_full = bars + 2 * kEncMaxL;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kEncMaxL + 1);
+  uint64_t* store_done = bars + 2 * kEncMaxL + 1;           // control -> workers: the last activation store has left shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kEncMaxL + 2);
+  float* bias_s = reinterpret_cast<float*>(bars + 16);               // 128 bytes in: 16-byte aligned   // [2][bias_n]: the agent's biases, double-buffered
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int l = 0; l < kEncMaxL; ++l) { mbar_init(act_ready + l, kEncWorkers); mbar_init(mma_done + l, 1); }
     mbar_init(w_full, 1);
+    mbar_init(store_done, 1);
     fence_barrier_init();
   }
   if (warp == 8) {
@@ -108,20 +121,25 @@ enc_fwd_kernel(const __grid_constant__ EncMaps maps, const EncFwdParams p) {
         for (int l = 0; l < nl; ++l) {
           mbar_wait(act_ready + l, par);
           tc_fence_after();
-          // layer l's input tile: out to HBM for the backward pass, while the MMAs below read the same bytes
-          for (int kb = 0; kb < p.kboxes[l]; ++kb) tma_store_3d(&maps.x[l], act + kb * kBoxBytes, kb * 64, t * kEncRows, a);
-          tma_store_commit();
+          const uint32_t in_s = act_s + p.in_box[l] * kBoxBytes;
+          {              // layer l's input tile: out to HBM for the backward pass while the MMAs below read the same bytes
+            for (int kb = 0; kb < p.kboxes[l]; ++kb)
+              tma_store_3d(&maps.x[l], act + (p.in_box[l] + kb) * kBoxBytes, kb * 64, t * kEncRows, a);
+            tma_store_commit();
+          }
           const uint32_t idesc = make_idesc(kEncRows, p.N[l], false, false);
           const uint32_t wl = w_s + p.w_off[l];
           const uint32_t nbox = static_cast<uint32_t>(p.N[l]) * 128u;
           for (int ks = 0; ks < p.ksteps[l]; ++ks) {
-            const uint64_t da = make_smem_desc(act_s + (ks >> 2) * kBoxBytes + (ks & 3) * 32, 16u, 1024u);
+            const uint64_t da = make_smem_desc(in_s + (ks >> 2) * kBoxBytes + (ks & 3) * 32, 16u, 1024u);
             const uint64_t db = make_smem_desc(wl + (ks >> 2) * nbox + (ks & 3) * 32, 16u, 1024u);
             umma_bf16(tmem_base + p.tmem_col[l], da, db, idesc, ks > 0 ? 1u : 0u);
           }
-          tma_store_wait_read();               // the store engine is done with the tile: the epilogue may overwrite it
+          if (p.wait_store[l]) tma_store_wait_read();   // this layer's epilogue writes over boxes a store may still be reading
           umma_commit(mma_done + l);
         }
+        tma_store_wait_read();
+        mbar_arrive(store_done);                        // the next unit's X0 may overwrite the activation boxes
         mbar_wait(mma_done + (nl - 1), par);
       }
       tma_store_wait_all();
@@ -131,100 +149,133 @@ enc_fwd_kernel(const __grid_constant__ EncMaps maps, const EncFwdParams p) {
     const int q = warp & 3, half = warp >> 2;
     const int row = q * 32 + lane;                                   // tile row == TMEM lane
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const int nchunk0 = p.kboxes[0] * 8;                             // 16-byte chunks per X0 row
-    int cur_a = -1, od = 0, off = 0;
-    uint4 emb_pk = make_uint4(0, 0, 0, 0);
-    uint32_t par = 0;
-    for (int u = u0; u < u1; ++u, par ^= 1) {
+    const int nchunk0 = p.kboxes[0] * 8;                             // 16-byte chunks per X0 row held in shared memory
+    const int col0 = lane * 8;                                       // this lane's X0 columns [col0, col0 + 8)
+    uint8_t* const x0box = act + (lane >> 3) * kBoxBytes;
+    // staging state of the unit being prefetched: lane role + packed bf16 chunks of its 16 rows (warp + 8 i)
+    StageLane sl;
+    float raw[8][8];
+    int st_a = -1, st_bias = 0;
+    auto stage_setup = [&](int u) {
       const int a = u / p.tiles, t = u - a * p.tiles;
-      const int b0 = t * kEncRows;
-      if (a != cur_a) {
-        cur_a = a; od = p.obs_dim[a]; off = p.obs_off[a];
-        if (!p.idx && lane * 8 < p.I) {
+      if (a != st_a) {
+        st_a = a;
+        // the agent's biases -> shared memory (the other buffer may still be in use by the unit in flight)
+        st_bias ^= 1;
+        float* bs = bias_s + st_bias * p.bias_n;
+        for (int l = 0; l < nl; ++l)
+          for (int i = threadIdx.x; i < p.N[l]; i += kEncWorkers) bs[p.tmem_col[l] + i] = __ldg(p.bias[l] + static_cast<long long>(a) * p.N[l] + i);
+        asm volatile("bar.sync 1, %0;" ::"n"(kEncWorkers) : "memory");
+        const int od = p.obs_dim[a];
+        sl.nvalid = min(8, od - (col0 - p.I));
+        sl.off = p.obs_off[a] + (col0 - p.I);
+        sl.emb = make_uint4(0, 0, 0, 0);
+        if (!p.idx && col0 < p.I) {
           float e[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) e[k] = __ldg(p.idx_emb + static_cast<long long>(a) * p.I + lane * 8 + k);
-          emb_pk = pack8(e);
+          for (int k = 0; k < 8; ++k) e[k] = __ldg(p.idx_emb + static_cast<long long>(a) * p.I + col0 + k);
+          sl.emb = pack8(e);
         }
       }
-      // ---- X0 = [idx_emb | obs_a | 0]: warp w builds rows w, w + 8, ...; lane = 16-byte chunk (8 columns) of the row ----
+      sl.a = a; sl.b0 = t * kEncRows;
+      sl.src0 = p.obs + static_cast<long long>(sl.b0) * p.obs_ld + sl.off;
+      sl.kind = kStageNone;
       if (lane < nchunk0) {
-        const int col0 = lane * 8;
-        const int j0 = col0 - p.I;
-        uint8_t* box = act + (lane >> 3) * kBoxBytes;
-#pragma unroll 1
-        for (int rr = 0; rr < kEncRows / 8; rr += 4) {
-          uint4 val[4];
+        if (col0 < p.I) sl.kind = p.idx ? kStageEmbIdx : kStageEmb;
+        else if (sl.nvalid > 0 && ((reinterpret_cast<uintptr_t>(sl.src0) | (static_cast<uintptr_t>(p.obs_ld) << 2)) & 7) == 0) sl.kind = kStageVec;
+        else if (sl.nvalid > 0) sl.kind = kStageScalar;
+        else sl.kind = kStageZero;
+      }
+    };
+    // global loads of half h (rows warp + 8 (8 h + i)) into `raw`: straight-line, all in flight together
+    auto stage_load = [&](int h) {
+      if (sl.kind == kStageVec) {
+        // 8-byte loads; the lane at the end of the agent's slice predicates the pairs past it (never reads beyond the row)
+        const int npair = sl.nvalid >> 1;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = warp + 8 * (rr + i);
-            const long long b = b0 + r;
-            val[i] = make_uint4(0, 0, 0, 0);
-            if (b < p.B) {
-              if (col0 < p.I) {
-                if (p.idx) {
-                  const int id = static_cast<int>(p.idx[b * p.idx_ld + a]);
-                  float e[8];
+        for (int i = 0; i < 8; ++i) {
+          const int r = min(warp + 8 * (8 * h + i), p.B - 1 - sl.b0);     // rows past the batch re-read its last row
+          const float* src = sl.src0 + static_cast<long long>(r) * p.obs_ld;
 #pragma unroll
-                  for (int k = 0; k < 8; ++k) e[k] = __ldg(p.idx_emb + static_cast<long long>(id) * p.I + col0 + k);
-                  val[i] = pack8(e);
-                } else {
-                  val[i] = emb_pk;
-                }
-              } else if (j0 < od) {
-                const float* src = p.obs + b * p.obs_ld + off + j0;
-                float e[8];
-                if (j0 + 8 <= od && (reinterpret_cast<uintptr_t>(src) & 7) == 0) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const float2 v2 = __ldg(reinterpret_cast<const float2*>(src) + k);
-                    e[2 * k] = v2.x; e[2 * k + 1] = v2.y;
-                  }
-                } else {
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) e[k] = (j0 + k < od) ? __ldg(src + k) : 0.f;
-                }
-                val[i] = pack8(e);
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = warp + 8 * (rr + i);
-            *reinterpret_cast<uint4*>(box + sw128_chunk_off(r, lane & 7)) = val[i];
+          for (int k = 0; k < 4; ++k) {
+            float2 v2 = make_float2(0.f, 0.f);
+            if (k < npair) v2 = __ldg(reinterpret_cast<const float2*>(src) + k);
+            else if (2 * k < sl.nvalid) v2.x = __ldg(src + 2 * k);
+            raw[i][2 * k] = v2.x; raw[i][2 * k + 1] = v2.y;
           }
         }
+      } else if (sl.kind == kStageScalar) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = min(warp + 8 * (8 * h + i), p.B - 1 - sl.b0);
+          const float* src = sl.src0 + static_cast<long long>(r) * p.obs_ld;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) raw[i][k] = (k < sl.nvalid) ? __ldg(src + k) : 0.f;
+        }
+      } else if (sl.kind == kStageEmbIdx) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long b = min(static_cast<long long>(sl.b0 + warp + 8 * (8 * h + i)), static_cast<long long>(p.B - 1));
+          const int id = static_cast<int>(__ldg(p.idx + b * p.idx_ld + sl.a));
+#pragma unroll
+          for (int k = 0; k < 8; ++k) raw[i][k] = __ldg(p.idx_emb + static_cast<long long>(id) * p.I + col0 + k);
+        }
+      }
+    };
+    // pack half h and write it to shared memory (A operand of layer 0; the control thread TMA-stores the tile to HBM)
+    auto stage_store = [&](int h) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = warp + 8 * (8 * h + i);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (sl.kind == kStageEmb) v = sl.emb;
+        else if (sl.kind == kStageVec || sl.kind == kStageScalar || sl.kind == kStageEmbIdx) v = pack8(raw[i]);
+        if (sl.b0 + r >= p.B) v = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(x0box + sw128_chunk_off(r, lane & 7)) = v;
+      }
+    };
+
+    uint32_t par = 0;
+    for (int u = u0; u < u1; ++u, par ^= 1) {
+      stage_setup(u);
+      const int a = sl.a, b0 = sl.b0;
+      const float* const bias_u = bias_s + st_bias * p.bias_n;
+      // ---- X0 = [idx_emb | obs_a | 0]: two batches of 8 rows per warp, each one DRAM round trip ----
+      if (u > u0) mbar_wait(store_done, par ^ 1);                    // previous unit's last activation store has drained
+      if (sl.kind != kStageNone) {
+        stage_load(0); stage_store(0);
+        stage_load(1); stage_store(1);
       }
       fence_proxy_async();
       mbar_arrive(act_ready + 0);
 
-      // ---- hidden layers: accumulator -> +bias -> relu -> bf16 -> the next layer's A operand (in place) ----
+      // ---- hidden layers: accumulator -> +bias -> relu -> bf16 -> the next layer's A operand (in place) + HBM ----
       for (int l = 0; l + 1 < nl; ++l) {
         mbar_wait(mma_done + l, par);
         tc_fence_after();
         const int nch = p.N[l] >> 5;
-        const float* bias = p.bias[l] + static_cast<long long>(a) * p.N[l];
+        const float* bias = bias_u + p.tmem_col[l];
+        uint8_t* const outb = act + p.in_box[l + 1] * kBoxBytes;
         for (int c = half; c < nch; c += 2) {
           uint32_t v[32];
           tmem_ld32(lane_addr + p.tmem_col[l] + c * 32, v);
           tmem_ld_wait();
-          uint32_t pk[16];
+          uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c * 32) + j);
-            pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]) + bb.x, __uint_as_float(v[2 * j + 1]) + bb.y, true);
+            const float2 bb = reinterpret_cast<const float2*>(bias + c * 32)[j];
+            o[j] = pack_bf16x2(__uint_as_float(v[2 * j]) + bb.x, __uint_as_float(v[2 * j + 1]) + bb.y, true);
           }
-          uint8_t* box = act + (c >> 1) * kBoxBytes;
+          uint8_t* box = outb + (c >> 1) * kBoxBytes;
           const int ch0 = (c & 1) * 4;
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint4*>(box + sw128_chunk_off(row, ch0 + i)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            *reinterpret_cast<uint4*>(box + sw128_chunk_off(row, ch0 + i)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
         }
         tc_fence_before();
         fence_proxy_async();
         mbar_arrive(act_ready + l + 1);
       }
-
       // ---- last layer: (mu | logvar) -> LAT, z = mu + eps * exp(logvar / 2) -> ZIN, KL partial ----
       {
         const int l = nl - 1;
@@ -232,7 +283,7 @@ enc_fwd_kernel(const __grid_constant__ EncMaps maps, const EncFwdParams p) {
         tc_fence_after();
         const int L = p.L, hw = L >> 1;
         const int jh = half * hw;                                   // this warp's share of the latent columns
-        const float* bias = p.bias[l] + static_cast<long long>(a) * 2 * L;
+        const float* bias = bias_u + p.tmem_col[l];
         const long long b = b0 + row;
         const bool ok = b < p.B;
         float* latrow = p.lat + a * p.lat_gs + b * p.lat_ld;
@@ -248,8 +299,8 @@ enc_fwd_kernel(const __grid_constant__ EncMaps maps, const EncFwdParams p) {
             float mu[16], lv[16];
 #pragma unroll
             for (int k = 0; k < 16; k += 4) {
-              const float4 bm = __ldg(reinterpret_cast<const float4*>(bias + j + k));
-              const float4 bl = __ldg(reinterpret_cast<const float4*>(bias + L + j + k));
+              const float4 bm = *reinterpret_cast<const float4*>(bias + j + k);
+              const float4 bl = *reinterpret_cast<const float4*>(bias + L + j + k);
               mu[k] = __uint_as_float(vm[k]) + bm.x; mu[k + 1] = __uint_as_float(vm[k + 1]) + bm.y;
               mu[k + 2] = __uint_as_float(vm[k + 2]) + bm.z; mu[k + 3] = __uint_as_float(vm[k + 3]) + bm.w;
               lv[k] = __uint_as_float(vl[k]) + bl.x; lv[k + 1] = __uint_as_float(vl[k + 1]) + bl.y;
@@ -258,13 +309,18 @@ enc_fwd_kernel(const __grid_constant__ EncMaps maps, const EncFwdParams p) {
               *reinterpret_cast<float4*>(latrow + L + j + k) = make_float4(lv[k], lv[k + 1], lv[k + 2], lv[k + 3]);
             }
             float z[16];
+            float4 e4[4];                                            // branch hoisted: the four Philox calls interleave
+            if (p.eps) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) e4[k] = *reinterpret_cast<const float4*>(p.eps + b * p.eps_ld + a * L + j + 4 * k);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                e4[k] = philox_normal4(p.seed, p.step, static_cast<uint64_t>(p.sample0 + b), static_cast<uint32_t>((a * L + j + 4 * k) >> 2));
+            }
 #pragma unroll
             for (int k = 0; k < 16; k += 4) {
-              const int col = a * L + j + k;
-              float4 e;
-              if (p.eps) e = *reinterpret_cast<const float4*>(p.eps + b * p.eps_ld + col);
-              else       e = philox_normal4(p.seed, p.step, static_cast<uint64_t>(p.sample0 + b), static_cast<uint32_t>(col >> 2));
-              const float ev[4] = {e.x, e.y, e.z, e.w};
+              const float ev[4] = {e4[k >> 2].x, e4[k >> 2].y, e4[k >> 2].z, e4[k >> 2].w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float s = expf(0.5f * lv[k + i]);
@@ -313,7 +369,7 @@ bool enc_fused_applicable(const EncFusedDesc& d) {
     wbytes += static_cast<size_t>((K + 63) / 64) * N * 128;
   }
   if (cols > kEncTmemCols) return false;
-  if (kActBoxes * kBoxBytes + wbytes + 256 + 1024 > kEncSmemLimit) return false;
+  if (kActBoxes * kBoxBytes + wbytes + 256 + 2 * cols * sizeof(float) + 1024 > kEncSmemLimit) return false;
   return true;
 }
 
@@ -331,15 +387,27 @@ int enc_fused_plan(const EncFusedDesc& d, EncFusedPlan** out) {
     p.w_off[l] = woff; woff += static_cast<uint32_t>(p.kboxes[l]) * N * 128;
     p.bias[l] = d.bias[l];
     rc = encode_tmap_bf16_3d(&pl->fmaps.w[l], d.W[l], K, N, d.A, K, static_cast<int64_t>(N) * K, 64, N);
+    p.xout[l] = static_cast<__nv_bfloat16*>(d.X[l]); p.xout_gs[l] = d.x_gs[l]; p.xout_ld[l] = d.x_ld[l]; p.xout_w[l] = K;
     if (rc == 0) rc = encode_tmap_bf16_3d(&pl->fmaps.x[l], d.X[l], K, d.B, d.A, d.x_ld[l], d.x_gs[l], 64, kEncRows);
+    // activation boxes: X0 starts at box 0; a hidden activation goes next to the tile whose TMA store may still be in
+    // flight when it is written, or back to box 0 (then the control thread drains that store first)
+    if (l == 0) p.in_box[0] = 0;
+    if (l + 1 < d.nl) {
+      const int in_end = p.in_box[l] + p.kboxes[l];                         // boxes a pending store may be reading
+      const int nb_out = N / 64;
+      if (in_end + nb_out <= kActBoxes) { p.in_box[l + 1] = in_end; p.wait_store[l] = 0; }
+      else { p.in_box[l + 1] = 0; p.wait_store[l] = 1; }
+    } else {
+      p.wait_store[l] = 0;
+    }
   }
   if (rc != 0) { delete pl; return rc; }
-  p.w_bytes = woff;
+  p.w_bytes = woff; p.bias_n = col;
   p.obs_off = d.obs_off; p.obs_dim = d.obs_dim; p.idx_emb = d.idx_emb; p.I = d.I;
   p.lat = d.lat; p.lat_gs = d.lat_gs; p.lat_ld = d.lat_ld;
   p.zin = static_cast<__nv_bfloat16*>(d.zin); p.zin_ld = d.zin_ld; p.L = d.L;
   pl->grid = std::min(p.total_units, kNumSMs);
-  pl->fwd_smem = static_cast<size_t>(kActBoxes) * kBoxBytes + woff + 256 + 1024;
+  pl->fwd_smem = static_cast<size_t>(kActBoxes) * kBoxBytes + woff + 256 + 2 * col * sizeof(float) + 1024;
   *out = pl;
   return 0;
 }

@@ -75,6 +75,9 @@ struct MfvaeHandle_ {
   cudaStream_t side = nullptr;
   std::vector<cudaEvent_t> fork_ev;
   cudaEvent_t join_ev = nullptr;
+  // third stream: the reward head (two tiny GEMM chains) and the action-embedding kernels run beside the big layers
+  cudaStream_t aux = nullptr;
+  cudaEvent_t aux_fork_ev = nullptr, aux_join_ev = nullptr, aux_fork2_ev = nullptr, aux_join2_ev = nullptr;
   cudaStream_t opt_stream = nullptr;         // overlapped Adam
   cudaEvent_t opt_ev = nullptr, dec_read_ev = nullptr;
 
@@ -341,7 +344,7 @@ static int build_ops(MfvaeHandle_* h) {
     for (size_t i = 0; i < h->gemms.size(); ++i) MFVAE_TRY(gemm_tc_plan(h->gemms[i], &h->tc[i]));
   }
   // ---- fused encoder chain ----
-  if (h->use_tc && h->cfg.fusion == MFVAE_FUSE_AUTO && h->ne <= kEncMaxL) {
+  if (h->use_tc && h->cfg.fusion == MFVAE_FUSE_ENCODER && h->ne <= kEncMaxL) {
     EncFusedDesc d;
     d.A = A; d.B = B; d.nl = h->ne; d.I = h->I; d.L = h->L; d.K0p = h->K0p;
     for (int l = 0; l < h->ne; ++l) {
@@ -380,11 +383,36 @@ static int check_ready(MfvaeHandle_* h, const MfvaeBatch* b) {
 static float* losses_ptr(MfvaeHandle_* h) { return reinterpret_cast<float*>(h->ws + h->off_losses); }
 static float* scratch_ptr(MfvaeHandle_* h, int i) { return reinterpret_cast<float*>(h->ws + h->off_scratch) + 4096 * i; }
 
+static bool use_aux(const MfvaeHandle_* h) { return h->aux != nullptr && !h->profiling; }
+
+// action-embedding half of the decoder input: independent of the encoders, so it runs beside them on the aux stream
+static int do_forward_act_embed(MfvaeHandle_* h, const StageArgs& st, cudaStream_t s) {
+  if (!use_aux(h)) return launch_stage(st, s, false, true);
+  MFVAE_CUDA(cudaEventRecord(h->aux_fork_ev, s));          // orders it after whatever last read ZIN on the caller's stream
+  MFVAE_CUDA(cudaStreamWaitEvent(h->aux, h->aux_fork_ev, 0));
+  MFVAE_TRY(launch_stage(st, h->aux, false, true));
+  MFVAE_CUDA(cudaEventRecord(h->aux_join_ev, h->aux));
+  return 0;
+}
+
 static int do_forward_decoders(MfvaeHandle_* h, cudaStream_t s) {
+  const bool aux = use_aux(h);
+  if (aux) MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join_ev, 0));     // action embeddings are in ZIN
   for (int l = 0; l < h->cfg.n_dec_hidden; ++l) MFVAE_TRY(run_gemm(h, h->g_dec_fwd[l], s));
+  // reward head (two tiny GEMMs) beside the state output layer
+  cudaStream_t r = s;
+  if (aux) {
+    MFVAE_CUDA(cudaEventRecord(h->aux_fork2_ev, s));
+    MFVAE_CUDA(cudaStreamWaitEvent(h->aux, h->aux_fork2_ev, 0));
+    r = h->aux;
+  }
   MFVAE_TRY(run_gemm(h, h->g_sout_fwd, s));
-  MFVAE_TRY(run_gemm(h, h->g_rout_fwd, s));
-  MFVAE_TRY(run_gemm(h, h->g_rl_fwd, s));
+  MFVAE_TRY(run_gemm(h, h->g_rout_fwd, r));
+  MFVAE_TRY(run_gemm(h, h->g_rl_fwd, r));
+  if (aux) {
+    MFVAE_CUDA(cudaEventRecord(h->aux_join2_ev, h->aux));
+    MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join2_ev, 0));
+  }
   return 0;
 }
 
@@ -406,7 +434,7 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
   }
   if (h->enc_fused) {
     // staging of X0, the four encoder layers, reparameterisation and KL: one kernel (enc_fused.cu)
-    MFVAE_TRY(launch_stage(st, s, false, true));
+    MFVAE_TRY(do_forward_act_embed(h, st, s));
     EncFwdBatch eb{};
     eb.obs = b->d_obs; eb.obs_ld = h->S; eb.idx = b->d_idx; eb.idx_ld = h->A;
     eb.eps = b->d_eps; eb.eps_ld = static_cast<int64_t>(h->A) * h->L; eb.seed = b->seed; eb.step = b->step; eb.sample0 = b->sample0;
@@ -414,7 +442,8 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
     MFVAE_TRY(enc_fused_forward(h->enc_fused, eb, s));
     return do_forward_decoders(h, s);
   }
-  MFVAE_TRY(launch_stage(st, s));
+  MFVAE_TRY(do_forward_act_embed(h, st, s));
+  MFVAE_TRY(launch_stage(st, s, true, false));
   for (int l = 0; l < h->ne; ++l) MFVAE_TRY(run_gemm(h, h->g_enc_fwd[l], s));
   ReparamArgs rp{};
   rp.mu = lat; rp.lv = lat + h->L; rp.lat_as = h->LAT.gs; rp.lat_bs = h->LAT.ld;
@@ -491,18 +520,34 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
     }
   }
   MFVAE_TRY(fork());                                            // D(recon_s), D(recon_r) and the zeroed arena are ready
+  // reward head: reward_linear and the reward decoder's output layer are tiny; their whole backward chain runs on the
+  // aux stream beside the state output layer (which owns the SMs for ~70 us on each of the other two streams)
+  const bool auxo = overlap && h->aux != nullptr;
+  cudaStream_t r = auxo ? h->aux : s, rw = auxo ? h->aux : w;
+  if (auxo) {
+    MFVAE_CUDA(cudaEventRecord(h->aux_fork_ev, s));
+    MFVAE_CUDA(cudaStreamWaitEvent(h->aux, h->aux_fork_ev, 0));
+  }
   // output layers + reward_linear
   MFVAE_TRY(run_gemm(h, h->g_sout_wg, w));
   MFVAE_TRY(launch_colsum(ws + h->DRS.off, dt, 1, h->B, h->S, h->DRS.ld, 0, G + h->sOutB.off, 0, w));
-  MFVAE_TRY(run_gemm(h, h->g_rl_wg, w));
-  MFVAE_TRY(launch_colsum(ws + h->DRR.off, dt, 1, h->B, A, h->DRR.ld, 0, G + h->rlb.off, 0, w));
   MFVAE_TRY(run_gemm(h, h->g_sout_dg, s));
-  MFVAE_TRY(run_gemm(h, h->g_rl_dg, s));
-  MFVAE_TRY(fork());                                            // D(reward decoder output) ready
-  MFVAE_TRY(run_gemm(h, h->g_rout_wg, w));
-  MFVAE_TRY(launch_colsum(ws + h->DRR0.off, dt, 1, h->B, A, h->DRR0.ld, 0, G + h->rOutB.off, 0, w));
+  MFVAE_TRY(run_gemm(h, h->g_rl_dg, r));
+  MFVAE_TRY(run_gemm(h, h->g_rout_dg, r));
+  if (auxo) {                                                   // D of the last hidden layer: state half (s) + reward half (aux)
+    MFVAE_CUDA(cudaEventRecord(h->aux_join_ev, h->aux));
+    MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join_ev, 0));
+  }
+  MFVAE_TRY(run_gemm(h, h->g_rl_wg, rw));
+  MFVAE_TRY(launch_colsum(ws + h->DRR.off, dt, 1, h->B, A, h->DRR.ld, 0, G + h->rlb.off, 0, rw));
+  if (!auxo) MFVAE_TRY(fork());                                 // D(reward decoder output) from the dgrad chain
+  MFVAE_TRY(run_gemm(h, h->g_rout_wg, rw));
+  MFVAE_TRY(launch_colsum(ws + h->DRR0.off, dt, 1, h->B, A, h->DRR0.ld, 0, G + h->rOutB.off, 0, rw));
+  if (auxo) {
+    MFVAE_CUDA(cudaEventRecord(h->aux_join2_ev, h->aux));
+    MFVAE_CUDA(cudaStreamWaitEvent(w, h->aux_join2_ev, 0));
+  }
   MFVAE_CUDA(cudaEventRecord(h->buckets[0].ev, w));
-  MFVAE_TRY(run_gemm(h, h->g_rout_dg, s));
   // decoder hidden layers, last to first
   for (int l = nh - 1; l >= 0; --l) {
     MFVAE_TRY(fork());                                          // D_l (both decoder halves) ready
@@ -515,8 +560,15 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
   MFVAE_CUDA(cudaEventRecord(h->buckets[2].ev, w));
   if (h->dec_read_ev) MFVAE_CUDA(cudaEventRecord(h->dec_read_ev, s));   // last reader of the decoder weights (dgrad layer 0) is queued
   // action tables (model.py:121: unregistered; gradients still flow)
+  cudaStream_t at = s;
+  if (auxo) {
+    MFVAE_CUDA(cudaEventRecord(h->aux_fork2_ev, s));            // GZIN is complete
+    MFVAE_CUDA(cudaStreamWaitEvent(h->aux, h->aux_fork2_ev, 0));
+    at = h->aux;
+  }
   MFVAE_TRY(launch_act_table_grad(ws + h->GZIN.off, dt, h->GZIN.ld, A * h->L, b->d_act, A, h->d_meta + 2 * A, A, h->C, h->B,
-                                  G + h->actT.off, static_cast<int64_t>(h->nact_max) * h->C, s));
+                                  G + h->actT.off, static_cast<int64_t>(h->nact_max) * h->C, at));
+  if (auxo) MFVAE_CUDA(cudaEventRecord(h->aux_join_ev, h->aux));
   // reparameterization + KL backward
   ReparamBwdArgs rb{};
   const float* lat = reinterpret_cast<const float*>(ws + h->LAT.off);
@@ -544,6 +596,7 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
   if (overlap) {                                               // join
     MFVAE_CUDA(cudaEventRecord(h->join_ev, w));
     MFVAE_CUDA(cudaStreamWaitEvent(s, h->join_ev, 0));
+    if (auxo) MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join_ev, 0));
   }
   for (size_t i = 3; i < h->buckets.size(); ++i) MFVAE_CUDA(cudaEventRecord(h->buckets[i].ev, s));
   return 0;
@@ -594,6 +647,11 @@ int mfvae_create(const MfvaeConfig* cfg, int device, MfvaeHandle* out) {
     h->fork_ev.push_back(e);
   }
   cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming);
+  if (cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess) h->aux = nullptr;
+  cudaEventCreateWithFlags(&h->aux_fork_ev, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->aux_join_ev, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->aux_fork2_ev, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->aux_join2_ev, cudaEventDisableTiming);
   if (cudaStreamCreateWithFlags(&h->opt_stream, cudaStreamNonBlocking) != cudaSuccess) h->opt_stream = nullptr;
   cudaEventCreateWithFlags(&h->opt_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->dec_read_ev, cudaEventDisableTiming);
@@ -617,6 +675,8 @@ int mfvae_destroy(MfvaeHandle h) {
   for (auto e : h->fork_ev) if (e) cudaEventDestroy(e);
   if (h->join_ev) cudaEventDestroy(h->join_ev);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->aux) cudaStreamDestroy(h->aux);
+  for (cudaEvent_t e : {h->aux_fork_ev, h->aux_join_ev, h->aux_fork2_ev, h->aux_join2_ev}) if (e) cudaEventDestroy(e);
   if (h->opt_ev) cudaEventDestroy(h->opt_ev);
   if (h->dec_read_ev) cudaEventDestroy(h->dec_read_ev);
   if (h->opt_stream) cudaStreamDestroy(h->opt_stream);

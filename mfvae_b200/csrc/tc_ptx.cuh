@@ -126,6 +126,32 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr) : "memory");
 }
 
+// One lane holds 32 consecutive bf16 (64 bytes, o[16]) of tile row `row`; the warp's 32 lanes hold 32 consecutive rows.
+// A lane can move 16 bytes per store, so lanes (2i, 2i+1) trade halves and every instruction writes whole 32-byte
+// sectors: half as many L2 write sectors as 32 row-strided 16-byte pieces.  `c` points at (tile row 0, first column);
+// rows >= rows_valid are not written.  Every lane of the warp must call this (it shuffles).
+__device__ __forceinline__ void store_bf16_row32(__nv_bfloat16* c, long long ld, int row, int rows_valid, int lane,
+                                                 const uint32_t (&o)[16]) {
+  const bool odd = lane & 1;
+  uint32_t rc[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    rc[i] = __shfl_xor_sync(0xffffffffu, odd ? o[i] : o[4 + i], 1);
+    rc[4 + i] = __shfl_xor_sync(0xffffffffu, odd ? o[8 + i] : o[12 + i], 1);
+  }
+  const int row_e = row & ~1;
+  __nv_bfloat16* ce = c + static_cast<long long>(row_e) * ld + (odd ? 8 : 0);
+  __nv_bfloat16* co = ce + ld;
+  if (row_e < rows_valid) {
+    *reinterpret_cast<uint4*>(ce) = odd ? make_uint4(rc[0], rc[1], rc[2], rc[3]) : make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(ce + 16) = odd ? make_uint4(rc[4], rc[5], rc[6], rc[7]) : make_uint4(o[8], o[9], o[10], o[11]);
+  }
+  if (row_e + 1 < rows_valid) {
+    *reinterpret_cast<uint4*>(co) = odd ? make_uint4(o[4], o[5], o[6], o[7]) : make_uint4(rc[0], rc[1], rc[2], rc[3]);
+    *reinterpret_cast<uint4*>(co + 16) = odd ? make_uint4(o[12], o[13], o[14], o[15]) : make_uint4(rc[4], rc[5], rc[6], rc[7]);
+  }
+}
+
 // byte offset of element (row, col) inside one 128B-swizzled box of [rows][64] bf16 (rows x 128 bytes, 1024-byte aligned):
 // the 16-byte chunk index is XOR-ed with (row % 8) -- the layout TMA SWIZZLE_128B writes and the UMMA descriptors read
 __device__ __forceinline__ uint32_t sw128_chunk_off(int row, int chunk) {

@@ -1,4 +1,4 @@
-"""Fused kernels (fusion="auto") against the layer-by-layer kernels (fusion="none") of the same library on identical
+"""Fused kernels (fusion="encoder") against the layer-by-layer kernels (fusion="none") of the same library on identical
 weights, batch and Philox stream.  Both evaluate the same operations with the same bf16 rounding points, so they must
 agree far more tightly than either agrees with the fp32 oracle.  One JSON line; run in its own process:
 
@@ -24,12 +24,12 @@ def main(latent, B, explicit_idx=False):
     dev = "cuda:0"
     spec = O.simple_tag_spec(latent=latent)
     models = {}
-    for fusion in ("none", "auto"):
+    for fusion in ("none", "encoder"):
         torch.manual_seed(7)
         m = M.MAVAE(spec.idx_features, spec.latent, spec.act_features, True, spec.agents, spec.obs_dim, spec.n_act, dev,
                     precision="bf16", fusion=fusion, include_dead_decoder=False)
         models[fusion] = m
-    models["auto"].load_named(models["none"].named_arena_tensors())
+    models["encoder"].load_named(models["none"].named_arena_tensors())
     g = torch.Generator(device=dev).manual_seed(11)
     S, A = spec.state_dim, spec.n_agents
     obs = torch.randn(B, S, device=dev, generator=g)
@@ -54,7 +54,7 @@ def main(latent, B, explicit_idx=False):
         grads = {k: p.grad.clone() for k, p in m.named_arena_tensors().items()}
         params = {k: p.detach().clone() for k, p in m.named_arena_tensors().items()}
         res[fusion] = (fw, losses, grads, params)
-    fa, la, ga, pa = res["auto"]
+    fa, la, ga, pa = res["encoder"]
     fn, ln, gn, pn = res["none"]
     for k in fa:
         out["fwd_" + k] = rel(fa[k], fn[k])

@@ -4,9 +4,9 @@ with open(fn) as f:
     lines=[l for l in f if not l.startswith('==')]
 rows=[(r['Kernel Name'], float(r['Metric Value'])) for r in csv.DictReader(lines)]
 names=[n for n,_ in rows]
-starts=[i for i,n in enumerate(names) if 'stage_kernel' in n]
+starts=[i for i,n in enumerate(names) if 'act_embed_kernel' in n]
 print('captured', len(rows), 'step starts', starts[:8])
-i0=starts[2]; i1=starts[3]
+k=min(2,len(starts)-2); i0=starts[k]; i1=starts[k+1]
 step=rows[i0:i1]
 agg=collections.OrderedDict()
 for n,t in step:

@@ -32,11 +32,15 @@ enum { MFVAE_PREC_FP32 = 0, MFVAE_PREC_BF16 = 1 };
 /* GEMM engines.  AUTO = tcgen05 for bf16, SIMT FFMA for fp32.  SIMT with bf16 is a debugging aid that
  * runs the same data flow without tensor cores; it is NOT a fallback: nothing selects it implicitly. */
 enum { MFVAE_ENGINE_AUTO = 0, MFVAE_ENGINE_SIMT = 1, MFVAE_ENGINE_TCGEN05 = 2 };
-/* NONE = one kernel per layer.  ENCODER = staging + the per-agent encoder chain + reparameterisation + KL as ONE
- * persistent tcgen05 kernel (enc_fused.cu; falls back to per-layer kernels when its shape constraints do not hold).
- * AUTO = the variant that measured fastest on B200 (today: NONE).  All variants compute the
- * same values with the same rounding points. */
-enum { MFVAE_FUSE_AUTO = 0, MFVAE_FUSE_NONE = 1, MFVAE_FUSE_ENCODER = 2 };
+/* Cross-layer fusions of the tcgen05 engine (bit mask).  All variants compute the same values with the same rounding
+ * points; tests/test_gpu_fused.py pins them against each other.
+ *   NONE     one kernel per layer
+ *   ENCODER  staging + the per-agent encoder chain + reparameterisation + KL as ONE persistent tcgen05 kernel
+ *            (enc_fused.cu; per-layer kernels are used when its shape constraints do not hold)
+ *   LOSS     mfvae_fwd_bwd only: the state head's reconstruction loss and its gradient are the epilogue of the output-layer
+ *            GEMM (recon_s is never written to HBM; MfvaeOutputs.d_recon_s is NULL)
+ *   AUTO     the combination that measured fastest on B200 (today: NONE) */
+enum { MFVAE_FUSE_AUTO = 0, MFVAE_FUSE_NONE = 1, MFVAE_FUSE_ENCODER = 2, MFVAE_FUSE_LOSS = 4 };
 enum { MFVAE_LOSS_DEFAULT = 0, MFVAE_LOSS_HUBER = 1, MFVAE_LOSS_MSE = 2, MFVAE_LOSS_JOINT_MSE = 3 };
 
 typedef struct MfvaeConfig {
@@ -145,7 +149,8 @@ int mfvae_adam_step(MfvaeHandle h, float lr, float beta1, float beta2, float eps
 /* same update; the decoder block runs on an internal stream as soon as its gradient buckets are final (overlapping the
  * encoder half of backward).  Only valid when no collective has to run between backward and the update (1 GPU). */
 int mfvae_adam_step_overlapped(MfvaeHandle h, float lr, float beta1, float beta2, float eps, int64_t t, void* stream);
-/* forward + loss + backward in one call (no optimizer; the host all-reduces gradients in between) */
+/* forward + loss + backward in one call (no optimizer; the host all-reduces gradients in between).  With
+ * MFVAE_FUSE_LOSS out->d_recon_s is NULL (see above). */
 int mfvae_fwd_bwd(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* stream);
 
 /* instrumentation: number of kernels this library has launched so far (process-wide), and optional CUDA-event

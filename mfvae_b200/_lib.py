@@ -12,7 +12,7 @@ MAX_HIDDEN = 8
 
 PREC_FP32, PREC_BF16 = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
-FUSE_AUTO, FUSE_NONE, FUSE_ENCODER = 0, 1, 2
+FUSE_AUTO, FUSE_NONE, FUSE_ENCODER, FUSE_LOSS = 0, 1, 2, 4
 LOSS_DEFAULT, LOSS_HUBER, LOSS_MSE, LOSS_JOINT_MSE = 0, 1, 2, 3
 (T_IDX_EMB, T_ENC_W, T_ENC_B, T_ACT_TABLE, T_SDEC_W, T_SDEC_B, T_RDEC_W, T_RDEC_B, T_RLIN_W, T_RLIN_B) = range(10)
 

@@ -608,12 +608,20 @@ int launch_philox_normal(float* out, int64_t B, int width, uint64_t seed, uint64
   return 0;
 }
 
-__global__ void loss_total_kernel(float* losses, float r_weight, float kl_weight) {
-  losses[0] = losses[1] + r_weight * losses[2] + kl_weight * losses[3];
+__global__ void __launch_bounds__(kThreads) loss_total_kernel(float* losses, float r_weight, float kl_weight,
+                                                              const float* partials, int n_partials, float partial_scale) {
+  __shared__ float red[32];
+  if (partials) {                         // fixed summation order: the value is reproducible run to run
+    float v = 0.f;
+    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) v += __ldcg(partials + i);
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) losses[1] = v * partial_scale;
+  }
+  if (threadIdx.x == 0) losses[0] = losses[1] + r_weight * losses[2] + kl_weight * losses[3];
 }
-
-int launch_loss_total(float* losses, float r_weight, float kl_weight, cudaStream_t s) {
-  loss_total_kernel<<<1, 1, 0, s>>>(losses, r_weight, kl_weight);
+int launch_loss_total(float* losses, float r_weight, float kl_weight, cudaStream_t s, const float* partials, int n_partials,
+                      float partial_scale) {
+  loss_total_kernel<<<1, kThreads, 0, s>>>(losses, r_weight, kl_weight, partials, n_partials, partial_scale);
   MFVAE_LAUNCH_CHECK();
   return 0;
 }

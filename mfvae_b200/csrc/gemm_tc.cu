@@ -47,6 +47,8 @@ struct TcParams {
   int epi;
   const __nv_bfloat16* aux; long long aux_gs, aux_ld;
   int accumulate_atomic;                  // split-K: red.global.add.f32
+  // kEpiLossGrad: C = d loss / d (A B^T + bias) against `tgt`, loss value accumulated per epilogue warp
+  const float* tgt; long long tgt_ld; float grad_scale; int huber; float* loss_partials;
 };
 
 template <int BN, int CPS> struct TcCfg {
@@ -63,14 +65,14 @@ template <int BN, int CPS> struct TcCfg {
 // epilogue for one 32-column chunk held by one thread (= one output row)
 // ------------------------------------------------------------------------------------------------
 // Every lane of the warp must call this (it shuffles); rows >= M only skip their loads / stores.
-__device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row, int col0, const uint32_t (&v)[32]) {
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row, int col0, const uint32_t (&v)[32], float& loss_acc) {
   const bool row_ok = row < p.M;
   const int ncols = min(32, p.N - col0);
   const int lane = threadIdx.x & 31;
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-  if (p.epi == kEpiBias || p.epi == kEpiBiasRelu) {
+  if (p.epi == kEpiBias || p.epi == kEpiBiasRelu || p.epi == kEpiLossGrad) {
     const float* b = p.bias + g * p.bias_gs + col0;
     if (ncols == 32) {
 #pragma unroll
@@ -100,6 +102,39 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row
 #pragma unroll
       for (int j = 0; j < 32; ++j) if (j < ncols && !(__bfloat162float(a[j]) > 0.f)) f[j] = 0.f;
     }
+  }
+  if (p.epi == kEpiLossGrad && row_ok) {
+    // reconstruction loss fused into the output layer (reference model.py:25-28): the reconstruction never goes to HBM,
+    // the epilogue reads the target, writes d loss / d recon and keeps the loss value
+    const float* t = p.tgt + static_cast<long long>(row) * p.tgt_ld + col0;
+    float tv[32];
+    if (ncols == 32 && (reinterpret_cast<uintptr_t>(t) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 t4 = ldg_stream4(t + j);
+        tv[j] = t4.x; tv[j + 1] = t4.y; tv[j + 2] = t4.z; tv[j + 3] = t4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tv[j] = (j < ncols) ? __ldg(t + j) : 0.f;
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float d = f[j] - tv[j];
+      float val, gr;
+      if (p.huber) {
+        const float ad = fabsf(d);
+        val = ad < 1.f ? 0.5f * d * d : ad - 0.5f;
+        gr = fminf(fmaxf(d, -1.f), 1.f) * p.grad_scale;
+      } else {
+        val = d * d;
+        gr = 2.f * d * p.grad_scale;
+      }
+      if (j < ncols) acc += val;
+      f[j] = gr;
+    }
+    loss_acc += acc;
   }
   const bool relu = (p.epi == kEpiBiasRelu);
   if (p.c_dtype == kBF16) {
@@ -275,6 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;              // which of the quarter's warps (0 .. kEpiWarps/4 - 1)
     int as = 0; uint32_t aphase = 0;
+    float loss_acc = 0.f;
     for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const int nt = static_cast<int>(w % p.n_tiles);
       const int mt = static_cast<int>((w / p.n_tiles) % p.m_tiles);
@@ -296,11 +332,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tmem_ld_wait();
           const bool more = (c + 2) < nchunks;
           if (more) tmem_ld32(taddr + (c + 2) * 32, vb);
-          epilogue_chunk(p, g, row, nt * BN + c * 32, va);
+          epilogue_chunk(p, g, row, nt * BN + c * 32, va, loss_acc);
           if (more) {
             tmem_ld_wait();
             if (c + 4 < nchunks) tmem_ld32(taddr + (c + 4) * 32, va);
-            epilogue_chunk(p, g, row, nt * BN + (c + 2) * 32, vb);
+            epilogue_chunk(p, g, row, nt * BN + (c + 2) * 32, vb, loss_acc);
           }
         }
       } else {
@@ -309,7 +345,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int c = 0; c < nchunks; ++c) {
           tmem_ld32(taddr + c * 32, va);
           tmem_ld_wait();
-          epilogue_chunk(p, g, row, nt * BN + c * 32, va);
+          epilogue_chunk(p, g, row, nt * BN + c * 32, va, loss_acc);
         }
       }
       (void)kChunks;
@@ -317,6 +353,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + as);
       if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (p.epi == kEpiLossGrad) {            // one partial per epilogue warp; summed in fixed order by loss_total_kernel
+      loss_acc = warp_sum(loss_acc);
+      if (lane == 0) p.loss_partials[blockIdx.x * kEpiWarps + (warp - 2)] = loss_acc;
     }
   }
   tc_fence_before();
@@ -436,7 +476,8 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
   MFVAE_CHECK(reinterpret_cast<uintptr_t>(op.C) % 16 == 0, "tcgen05 GEMM: C must be 16-byte aligned");
   MFVAE_CHECK(op.epi != kEpiReluMask || (op.aux && op.aux_ld % 8 == 0 && op.aux_gs % 8 == 0 && reinterpret_cast<uintptr_t>(op.aux) % 16 == 0),
               "tcgen05 GEMM: relu-mask aux alignment");
-  MFVAE_CHECK((op.epi != kEpiBias && op.epi != kEpiBiasRelu) || (op.bias && reinterpret_cast<uintptr_t>(op.bias) % 16 == 0 && op.bias_gs % 4 == 0),
+  MFVAE_CHECK(op.epi != kEpiLossGrad || (op.c_dtype == kBF16 && op.split_k == 1), "tcgen05 GEMM: the loss epilogue writes bf16 gradients, no split-K");
+  MFVAE_CHECK((op.epi != kEpiBias && op.epi != kEpiBiasRelu && op.epi != kEpiLossGrad) || (op.bias && reinterpret_cast<uintptr_t>(op.bias) % 16 == 0 && op.bias_gs % 4 == 0),
               "tcgen05 GEMM: bias alignment");
   TcPlan* pl = new TcPlan();
   pl->op = op;
@@ -475,6 +516,7 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
   p.C = op.C; p.c_gs = op.c_gs; p.c_ld = op.c_ld; p.c_dtype = op.c_dtype;
   p.bias = op.bias; p.bias_gs = op.bias_gs; p.epi = op.epi;
   p.aux = static_cast<const __nv_bfloat16*>(op.aux); p.aux_gs = op.aux_gs; p.aux_ld = op.aux_ld;
+  p.tgt = nullptr; p.tgt_ld = 0; p.grad_scale = 0.f; p.huber = 1; p.loss_partials = nullptr;
   p.accumulate_atomic = (op.epi == kEpiAccum && splits > 1) ? 1 : 0;   // single split: plain stores into the zeroed C
   pl->BN = BN;
   pl->grid = static_cast<int>(std::min<long long>(p.total_work, static_cast<long long>(kNumSMs) * pl->cps));
@@ -497,6 +539,16 @@ int gemm_tc_run(const TcPlan* pl, cudaStream_t s) {
 }
 
 void gemm_tc_free(TcPlan* p) { delete p; }
+
+int gemm_tc_set_loss(TcPlan* pl, const float* tgt, int64_t tgt_ld, float grad_scale, int huber, float* partials) {
+  MFVAE_CHECK(pl && pl->prm.epi == kEpiLossGrad, "tcgen05 GEMM: not a loss-epilogue plan");
+  pl->prm.tgt = tgt; pl->prm.tgt_ld = tgt_ld; pl->prm.grad_scale = grad_scale; pl->prm.huber = huber; pl->prm.loss_partials = partials;
+  return 0;
+}
+int gemm_tc_loss_partials(const TcPlan* pl) {
+  if (!pl) return 0;
+  return pl->grid * (pl->cps == 1 ? TcShape<1>::kEpiWarps : TcShape<3>::kEpiWarps);
+}
 bool gemm_tc_overwrites(const TcPlan* p) { return p && p->prm.accumulate_atomic == 0; }
 
 }  // namespace mfvae

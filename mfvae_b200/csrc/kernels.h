@@ -83,10 +83,12 @@ int launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream
 int launch_philox_normal(float* out, int64_t B, int width, uint64_t seed, uint64_t step, int64_t sample0,
                          cudaStream_t s);
 // losses[0] = s + r_w * r + kl_w * kl  given losses[1..3]
-int launch_loss_total(float* losses, float r_weight, float kl_weight, cudaStream_t s);
+// also sums `n_partials` per-warp partials of the fused output-layer loss into losses[1] (scaled) when partials != nullptr
+int launch_loss_total(float* losses, float r_weight, float kl_weight, cudaStream_t s, const float* partials = nullptr,
+                      int n_partials = 0, float partial_scale = 0.f);
 
 // ---- GEMM (gemm_simt.cu / gemm_tc.cu) --------------------------------------------------------
-enum Epilogue { kEpiNone = 0, kEpiBias = 1, kEpiBiasRelu = 2, kEpiReluMask = 3, kEpiAccum = 4 };
+enum Epilogue { kEpiNone = 0, kEpiBias = 1, kEpiBiasRelu = 2, kEpiReluMask = 3, kEpiAccum = 4, kEpiLossGrad = 5 };
 
 struct GemmOp {
   int G = 1, M = 0, N = 0, K = 0;
@@ -106,7 +108,10 @@ struct TcPlan;
 int gemm_tc_plan(const GemmOp& op, TcPlan** out);       // validates alignment, encodes CUtensorMaps
 int gemm_tc_run(const TcPlan* p, cudaStream_t s);
 void gemm_tc_free(TcPlan* p);
-bool gemm_tc_overwrites(const TcPlan* p);               // true: C is fully written by plain stores (no pre-zeroing needed)
+bool gemm_tc_overwrites(const TcPlan* p);
+// kEpiLossGrad plans: per-call target / scale / loss-partial buffer (one float per epilogue warp of the grid)
+int gemm_tc_set_loss(TcPlan* p, const float* tgt, int64_t tgt_ld, float grad_scale, int huber, float* partials);
+int gemm_tc_loss_partials(const TcPlan* p);               // true: C is fully written by plain stores (no pre-zeroing needed)
 
 // ---- fused per-agent encoder (enc_fused.cu) ---------------------------------------------------
 constexpr int kEncMaxL = 4;

@@ -69,6 +69,7 @@ struct MfvaeHandle_ {
   EncFusedPlan* enc_fused = nullptr;         // fused per-agent encoder chain (enc_fused.cu), when its shape constraints hold
   std::vector<int> g_enc_fwd, g_enc_wg, g_enc_dg, g_dec_fwd, g_dec_wg, g_dec_dg;
   int g_sout_fwd = -1, g_rout_fwd = -1, g_rl_fwd = -1;
+  int g_sout_loss = -1;                      // state output layer with the reconstruction loss + its gradient as the epilogue
   int g_sout_wg = -1, g_sout_dg = -1, g_rout_wg = -1, g_rout_dg = -1, g_rl_wg = -1, g_rl_dg = -1;
 
   // side stream for the wgrad / bias-gradient chain of backward, with its fork / join events
@@ -330,6 +331,10 @@ static int build_ops(MfvaeHandle_* h) {
     char* dhs = ws + h->DHD[nh - 1].off; char* dhr = dhs + static_cast<int64_t>(HL) * es;
     const int64_t hld = h->HD[nh - 1].ld;
     h->g_sout_fwd = fwd(1, B, h->S, HL, hs, 0, hld, wptr(h->sOutW.off), 0, HL, buf(h->RS), 0, h->RS.ld, kF32, P + h->sOutB.off, 0, false);
+    if (h->use_tc) {
+      h->g_sout_loss = fwd(1, B, h->S, HL, hs, 0, hld, wptr(h->sOutW.off), 0, HL, buf(h->DRS), 0, h->DRS.ld, dt, P + h->sOutB.off, 0, false);
+      h->gemms[h->g_sout_loss].epi = kEpiLossGrad;
+    }
     h->g_rout_fwd = fwd(1, B, A, HL, hr, 0, hld, wptr(h->rOutW.off), 0, HL, buf(h->RR0), 0, h->RR0.ld, dt, P + h->rOutB.off, 0, false);
     h->g_rl_fwd = fwd(1, B, A, A, buf(h->RR0), 0, h->RR0.ld, wptr(h->rlW.off), 0, h->Ap, buf(h->RR), 0, h->RR.ld, kF32, P + h->rlb.off, 0, false);
     h->g_rl_wg = wgrad(1, A, A, buf(h->DRR), 0, h->DRR.ld, buf(h->RR0), 0, h->RR0.ld, h->rlW.off, 0, h->Ap);
@@ -344,7 +349,7 @@ static int build_ops(MfvaeHandle_* h) {
     for (size_t i = 0; i < h->gemms.size(); ++i) MFVAE_TRY(gemm_tc_plan(h->gemms[i], &h->tc[i]));
   }
   // ---- fused encoder chain ----
-  if (h->use_tc && h->cfg.fusion == MFVAE_FUSE_ENCODER && h->ne <= kEncMaxL) {
+  if (h->use_tc && (h->cfg.fusion & MFVAE_FUSE_ENCODER) && h->ne <= kEncMaxL) {
     EncFusedDesc d;
     d.A = A; d.B = B; d.nl = h->ne; d.I = h->I; d.L = h->L; d.K0p = h->K0p;
     for (int l = 0; l < h->ne; ++l) {
@@ -395,7 +400,9 @@ static int do_forward_act_embed(MfvaeHandle_* h, const StageArgs& st, cudaStream
   return 0;
 }
 
-static int do_forward_decoders(MfvaeHandle_* h, cudaStream_t s) {
+// loss_batch != nullptr (train step): the state output layer runs with the loss epilogue -- recon_s is not materialised,
+// D(recon_s) and the per-warp loss partials come straight out of the GEMM (the target must be bound in the batch).
+static int do_forward_decoders(MfvaeHandle_* h, cudaStream_t s, const MfvaeBatch* loss_batch = nullptr, int huber = 1) {
   const bool aux = use_aux(h);
   if (aux) MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join_ev, 0));     // action embeddings are in ZIN
   for (int l = 0; l < h->cfg.n_dec_hidden; ++l) MFVAE_TRY(run_gemm(h, h->g_dec_fwd[l], s));
@@ -406,7 +413,13 @@ static int do_forward_decoders(MfvaeHandle_* h, cudaStream_t s) {
     MFVAE_CUDA(cudaStreamWaitEvent(h->aux, h->aux_fork2_ev, 0));
     r = h->aux;
   }
-  MFVAE_TRY(run_gemm(h, h->g_sout_fwd, s));
+  if (loss_batch) {
+    const double cs = static_cast<double>(loss_batch->batch_global) * h->S;
+    MFVAE_TRY(gemm_tc_set_loss(h->tc[h->g_sout_loss], loss_batch->d_next, h->S, static_cast<float>(1.0 / cs), huber, scratch_ptr(h, 1)));
+    MFVAE_TRY(run_gemm(h, h->g_sout_loss, s));
+  } else {
+    MFVAE_TRY(run_gemm(h, h->g_sout_fwd, s));
+  }
   MFVAE_TRY(run_gemm(h, h->g_rout_fwd, r));
   MFVAE_TRY(run_gemm(h, h->g_rl_fwd, r));
   if (aux) {
@@ -416,8 +429,9 @@ static int do_forward_decoders(MfvaeHandle_* h, cudaStream_t s) {
   return 0;
 }
 
-static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, cudaStream_t s) {
+static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, cudaStream_t s, bool fuse_loss = false) {
   MFVAE_TRY(check_ready(h, b));
+  const MfvaeBatch* lb = fuse_loss ? b : nullptr;
   StageArgs st{};
   st.obs = b->d_obs; st.obs_ld = h->S; st.act = b->d_act; st.act_ld = h->A; st.idx = b->d_idx;
   st.idx_emb = h->ar.d_param + h->idx_emb.off;
@@ -431,6 +445,7 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
     out->d_recon_s = reinterpret_cast<const float*>(h->ws + h->RS.off); out->recon_s_ld = static_cast<int32_t>(h->RS.ld);
     out->d_recon_r = reinterpret_cast<const float*>(h->ws + h->RR.off); out->recon_r_ld = static_cast<int32_t>(h->RR.ld);
     out->d_latent = lat; out->d_losses = losses_ptr(h);
+    if (fuse_loss) { out->d_recon_s = nullptr; out->recon_s_ld = 0; }      // never written on this path
   }
   if (h->enc_fused) {
     // staging of X0, the four encoder layers, reparameterisation and KL: one kernel (enc_fused.cu)
@@ -440,7 +455,7 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
     eb.eps = b->d_eps; eb.eps_ld = static_cast<int64_t>(h->A) * h->L; eb.seed = b->seed; eb.step = b->step; eb.sample0 = b->sample0;
     eb.kl_scale = 1.0f / static_cast<float>(b->batch_global); eb.kl_out = losses_ptr(h) + 3; eb.scratch = scratch_ptr(h, 0);
     MFVAE_TRY(enc_fused_forward(h->enc_fused, eb, s));
-    return do_forward_decoders(h, s);
+    return do_forward_decoders(h, s, lb, h->cfg.huber);
   }
   MFVAE_TRY(do_forward_act_embed(h, st, s));
   MFVAE_TRY(launch_stage(st, s, true, false));
@@ -453,10 +468,10 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
   rp.kl_scale = 1.0f / static_cast<float>(b->batch_global);
   rp.kl_out = losses_ptr(h) + 3; rp.scratch = scratch_ptr(h, 0);
   MFVAE_TRY(launch_reparam_kl_fwd(rp, s));
-  return do_forward_decoders(h, s);
+  return do_forward_decoders(h, s, lb, h->cfg.huber);
 }
 
-static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStream_t s) {
+static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStream_t s, bool state_fused = false) {
   MFVAE_TRY(check_ready(h, b));
   MFVAE_CHECK(loss_kind >= MFVAE_LOSS_DEFAULT && loss_kind <= MFVAE_LOSS_JOINT_MSE, "unknown loss kind");
   const int joint_mse = (loss_kind == MFVAE_LOSS_JOINT_MSE);
@@ -474,14 +489,18 @@ static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStre
   a.huber = joint_mse ? 0 : use_huber;
   a.grad_scale = static_cast<float>(1.0 / cs); a.loss_scale = static_cast<float>(1.0 / cs);
   a.loss_out = losses_ptr(h) + 1; a.scratch = scratch_ptr(h, 1);
-  MFVAE_TRY(launch_recon_loss(a, s));
+  if (!state_fused) MFVAE_TRY(launch_recon_loss(a, s));
   a.recon = reinterpret_cast<const float*>(h->ws + h->RR.off); a.recon_ld = h->RR.ld;
   a.target = b->d_rew; a.target_ld = h->A;
   a.grad = h->ws + h->DRR.off; a.grad_ld = h->DRR.ld; a.width = h->A;
   a.grad_scale = static_cast<float>(static_cast<double>(rw) / cr); a.loss_scale = static_cast<float>(1.0 / cr);
   a.loss_out = losses_ptr(h) + 2; a.scratch = scratch_ptr(h, 2);
   MFVAE_TRY(launch_recon_loss(a, s));
-  MFVAE_TRY(launch_loss_total(losses_ptr(h), rw, h->cfg.kl_weight, s));
+  if (state_fused)
+    MFVAE_TRY(launch_loss_total(losses_ptr(h), rw, h->cfg.kl_weight, s, scratch_ptr(h, 1), gemm_tc_loss_partials(h->tc[h->g_sout_loss]),
+                                static_cast<float>(1.0 / cs)));
+  else
+    MFVAE_TRY(launch_loss_total(losses_ptr(h), rw, h->cfg.kl_weight, s));
   return 0;
 }
 
@@ -766,8 +785,10 @@ int mfvae_backward_ext(MfvaeHandle h, const MfvaeBatch* b, const float* d_g_reco
 int mfvae_fwd_bwd(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* stream) {
   MFVAE_CHECK(h, "null handle");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  MFVAE_TRY(do_forward(h, b, out, s));
-  MFVAE_TRY(do_loss(h, b, MFVAE_LOSS_DEFAULT, s));
+  // tensor-core engine: reconstruction loss of the state head fused into its output-layer GEMM (recon_s is not written)
+  const bool fuse = h->use_tc && (h->cfg.fusion & MFVAE_FUSE_LOSS) && h->g_sout_loss >= 0 && b && b->d_next && b->d_rew;
+  MFVAE_TRY(do_forward(h, b, out, s, fuse));
+  MFVAE_TRY(do_loss(h, b, MFVAE_LOSS_DEFAULT, s, fuse));
   return do_backward(h, b, s);
 }
 

@@ -236,7 +236,8 @@ class MAVAE(nn.Module):
         cfg.precision = {"fp32": L.PREC_FP32, "bf16": L.PREC_BF16}[precision]
         cfg.engine = {"auto": L.ENGINE_AUTO, "simt": L.ENGINE_SIMT, "tcgen05": L.ENGINE_TCGEN05}[engine]
         cfg.optimize_encoders = int(self.optimize_encoders)
-        cfg.fusion = {"auto": L.FUSE_AUTO, "none": L.FUSE_NONE, "encoder": L.FUSE_ENCODER}[fusion]
+        cfg.fusion = {"auto": L.FUSE_AUTO, "none": L.FUSE_NONE, "encoder": L.FUSE_ENCODER, "loss": L.FUSE_LOSS,
+                      "encoder+loss": L.FUSE_ENCODER | L.FUSE_LOSS}[fusion]
         self._cfg = cfg
         lib = L.lib()
         self._h = C.c_void_p()

@@ -27,12 +27,12 @@ def digest_err(got, want):
     return max(abs(got[1] - want[1]) / l2, float(np.abs(got[2:] - want[2:]).max() / scale))
 
 
-def main(case, precision, engine, mode="dropin", rng="eps"):
+def main(case, precision, engine, mode="dropin", rng="eps", fusion="auto"):
     spec, rec = load_case(case)
     dev = "cuda:0"
     huber = bool(rec["huber"])
     m = M.MAVAE(spec.idx_features, spec.latent, spec.act_features, True, spec.agents, spec.obs_dim, spec.n_act, dev,
-                precision=precision, engine=engine, huber=huber)
+                precision=precision, engine=engine, huber=huber, fusion=fusion)
     P = O.init_params(spec, int(rec["param_seed"]))
     m.load_named(P)
     st = O.OracleState(spec, {k: v.clone() for k, v in P.items() if not k.startswith("decoder.")})
@@ -81,9 +81,17 @@ def main(case, precision, engine, mode="dropin", rng="eps"):
         eps = {a: eps_all[:, i * L:(i + 1) * L] for i, a in enumerate(spec.agents)}
         if mode == "fast":
             # fast path = fwd+loss+bwd+adam in one call; compare losses and the post-step parameters only
+            Gq = None
+            if step == 0 and precision == "bf16":      # gradients of the fused step against the bf16-emulating oracle
+                _, Gq, _ = O.grads(st.P, spec, idx_state, acts, eps, nxt, rew, huber, emulate_bf16=True)
             losses_dev = m.train_step(pb, lr)
             sched.step()
             got_losses = [float(x) for x in losses_dev.cpu()]
+            if Gq is not None:
+                qerr = {k: rel_l2(p.grad, Gq[k]) for k, p in m.named_arena_tensors().items()}
+                qw = max(qerr, key=qerr.get)
+                out["grad_rel_max_vs_bf16_oracle"] = qerr[qw]; out["grad_rel_worst_vs_bf16_oracle"] = qw
+                out["grad_rel_median_vs_bf16_oracle"] = float(np.median(list(qerr.values())))
             o_losses, G, outs = O.train_step(st, idx_state, acts, eps, nxt, rew, lr, huber)
         else:
             got_losses = [float(loss), float(sl), float(rl), float(kl)]

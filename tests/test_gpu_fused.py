@@ -33,3 +33,6 @@ def test_fused_matches_layerwise(latent, batch, extra):
     assert max(o["loss_rel"]) < 1e-4, o
     # gradients: split-K / atomic accumulation orders differ between the two schedules
     assert o["grad_rel_median"] < 1e-3 and o["grad_rel_max"] < 2e-2, o
+    # loss fused into the output-layer epilogue vs the separate loss kernel: same fp32 values enter the same formula
+    assert o["lossfuse_loss_rel"] < 1e-5, o
+    assert o["lossfuse_grad_rel_max"] < 1e-3, o

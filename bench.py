@@ -41,6 +41,10 @@ WORKLOADS = {
     # BASELINE.json configs[0]: torch_ver/main.py default (B = 128, fp32)
     "cfg1": dict(latent=64, batch=128, enc_hidden=(64, 64, 256), dec_hidden=(1024, 256, 64, 256, 1024), precision="fp32",
                  name="cfg1: torch_ver/main.py default, batch 128, fp32"),
+    # BASELINE.json configs[3]: batches sampled from the jax_buffer-style replay buffer, batch 65536 over 8 GPUs.  The ring
+    # (HBM-resident, mfvae_ring_*) is sampled inside the timed region of every step: gather + train step.
+    "cfg4": dict(latent=64, batch=8192, enc_hidden=(64, 64, 256), dec_hidden=(1024, 256, 64, 256, 1024), precision="bf16", ring=True,
+                 name="cfg4: reference dims, batch 8192/GPU sampled every step from the HBM replay ring (65536 global at 8 GPUs), bf16"),
     # BASELINE.json configs[2]: wide MF-VAE
     "wide": dict(latent=128, batch=4096, enc_hidden=(1024, 1024, 1024, 1024), dec_hidden=(1024, 1024, 1024, 1024),
                  precision="bf16", name="cfg3: wide (hidden 1024 x4, latent 128) batch 4096/GPU, bf16"),
@@ -212,6 +216,23 @@ def run_ours(args, w):
         pb.sample0 = rank * B
         pb.batch_global = world * B
     lr = M.cosine_lr
+    ring = None
+    if w.get("ring"):
+        # this rank's shard of the replay ring: 4 batches of synthetic transitions in the ring's row layout
+        # [obs | act | next | rew | done]; every step draws B rows uniformly with replacement (Philox) and gathers them
+        from mfvae_b200.replay_buffer import DeviceRing
+        ring = DeviceRing(spec.agents, spec.obs_dim, capacity=nb * B, device=dev)
+        for pb in batches:
+            rows = torch.zeros(B, ring.row, device=dev)
+            rows[:, :2 * ring.S + 2 * ring.A] = torch.cat([pb.obs, pb.act, pb.next, pb.rew], dim=1)
+            ring.add_rows_device(rows)
+        torch.cuda.synchronize()
+        batches = None
+
+    def get_batch(i):
+        if ring is None:
+            return batches[i % nb]
+        return ring.sample_packed(B, seed=1234 + rank, sample0=rank * B, batch_global=world * B)
 
     def barrier():
         if world > 1:
@@ -220,7 +241,7 @@ def run_ours(args, w):
 
     # ---- device-resident timing (`value`) ----
     for i in range(args.warmup):
-        m.train_step(batches[i % nb], lr(i))
+        m.train_step(get_batch(i), lr(i))
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -229,26 +250,25 @@ def run_ours(args, w):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        losses = m.train_step(batches[i % nb], lr(args.warmup + i))
+        losses = m.train_step(get_batch(i), lr(args.warmup + i))
     e1.record()
     barrier()
     launches = L.lib().mfvae_launch_count() - launches0
-    if rank == 0:
-        # the timed region can be shorter than nvidia-smi's sampling period: keep the same load running (untimed)
-        # until a handful of samples exist, so the clocks / throttle reasons describe this workload under load
-        t_end = time.perf_counter() + 1.5
-        j = 0
-        while len(sampler.lines) < 8 and time.perf_counter() < t_end:
-            m.train_step(batches[j % nb], lr(j)); j += 1
-            if j % 20 == 0:
-                torch.cuda.synchronize()
-        torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
-    barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms)
+    # the timed region can be shorter than nvidia-smi's sampling period: keep the same load running (untimed) for ~1.2 s
+    # so the clocks / throttle reasons describe this workload under load.  The step contains collectives when N > 1, so
+    # EVERY rank runs the same number of extra steps (derived from the all-reduced step time).
+    n_extra = int(min(4000, max(20, 1.2e3 / max(ms_total / args.steps, 1e-3))))
+    for j in range(n_extra):
+        m.train_step(get_batch(j), lr(j))
+        if j % 50 == 49:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    barrier()
     value = world * B * args.steps / (ms_total * 1e-3)
     loss_host = [float(x) for x in losses.cpu()]
 
@@ -305,19 +325,20 @@ def run_ours(args, w):
     # ---- roofline of the tensor-core GEMMs, timed live with CUDA events on the launching stream ----
     roof = None
     pk = peaks()
+    L.check(L.lib().mfvae_profile_enable(m._h, 1))        # all ranks: the step holds collectives when N > 1
+    tim = (L.MfvaeGemmTiming * 256)()
+    acc = {}
+    reps = max(3, min(args.steps, 10))
+    for i in range(reps):
+        m.train_step(get_batch(i), lr(i))
+        n = L.lib().mfvae_profile_read(m._h, tim, 256)
+        for j in range(n):
+            t = tim[j]
+            key = (t.kind, t.groups, t.M, t.N, t.K, j)
+            acc.setdefault(key, []).append(t.ms)
+    L.check(L.lib().mfvae_profile_enable(m._h, 0))
+    barrier()
     if rank == 0:
-        L.check(L.lib().mfvae_profile_enable(m._h, 1))
-        tim = (L.MfvaeGemmTiming * 256)()
-        acc = {}
-        reps = max(3, min(args.steps, 10))
-        for i in range(reps):
-            m.train_step(batches[i % nb], lr(i))
-            n = L.lib().mfvae_profile_read(m._h, tim, 256)
-            for j in range(n):
-                t = tim[j]
-                key = (t.kind, t.groups, t.M, t.N, t.K, j)
-                acc.setdefault(key, []).append(t.ms)
-        L.check(L.lib().mfvae_profile_enable(m._h, 0))
         tot_ms, tot_fl, rows = 0.0, 0.0, []
         for (kind, G, Mm, Nn, Kk, j), v in acc.items():
             msj = float(np.mean(v)); fl = 2.0 * G * Mm * Nn * Kk
@@ -347,7 +368,8 @@ def run_ours(args, w):
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": w["precision"], "data": "synthetic",
                 "config": {"workload": w["name"], "batch_per_gpu": B, "global_batch": world * B,
-                           "parallelism": f"dp{world}", "l2": f"inputs {B * row * 4 / 1e6:.0f} MB/step, {nb} rotating device batches (> 126 MB L2)",
+                           "parallelism": f"dp{world}", "source": "replay ring (device gather every step)" if ring is not None else "device-resident batches",
+                           "l2": f"inputs {B * row * 4 / 1e6:.0f} MB/step, {nb} rotating device batches (> 126 MB L2)",
                            "flop_per_sample": flops_per_sample(spec)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * row * 4, "d2h_bytes_per_step": 16,
                         "steps": e2e_steps, "wall_s": wall, "api": "MAVAE.train_step(PackedBatch) fed from packed pinned host rows"},

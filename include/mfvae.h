@@ -53,7 +53,8 @@ typedef struct MfvaeConfig {
   int32_t n_dec_hidden;                  /* Decoder.HIDDEN  model.py:87 -> {1024,256,64,256,1024} */
   int32_t dec_hidden[MFVAE_MAX_HIDDEN];
   const int32_t* obs_dim;                /* [A] host, observation width per agent            */
-  const int32_t* n_act;                  /* [A] host, #discrete actions per agent            */
+  const int32_t* n_act;                  /* [A] host: the reference's action_dim dict -- #discrete actions per agent, or the
+                                            action-vector width per agent when continuous_act = 1                       */
   float kl_weight;                       /* model.py:5                                       */
   float r_weight;                        /* model.py:6                                       */
   int32_t huber;                         /* 1: Huber(delta=1) (model.py:25-31), 0: MSE       */
@@ -62,6 +63,9 @@ typedef struct MfvaeConfig {
   int32_t optimize_encoders;             /* 0 = reference semantics: encoders / action tables get
                                             gradients but no Adam update (model.py:112,114)  */
   int32_t fusion;                        /* MFVAE_FUSE_*: cross-layer kernel fusion (tcgen05 engine only)  */
+  int32_t continuous_act;                /* 0: nn.Embedding per agent (DESCRETE_ACT = True, model.py:121); 1: ActionEncoder MLP
+                                            action_dim -> act_hidden -> C per agent (model.py:60-74,123,148)                */
+  int32_t act_hidden;                    /* ActionEncoder.HIDDEN[0] (model.py:63: 64); 0 = 64                              */
 } MfvaeConfig;
 
 /* One tensor of the parameter arena.  Offsets are in ELEMENTS and identical for the fp32 master,
@@ -69,7 +73,7 @@ typedef struct MfvaeConfig {
  * (ld >= cols; padding columns are kept at zero). */
 enum { MFVAE_T_IDX_EMB = 0, MFVAE_T_ENC_W, MFVAE_T_ENC_B, MFVAE_T_ACT_TABLE,
        MFVAE_T_SDEC_W, MFVAE_T_SDEC_B, MFVAE_T_RDEC_W, MFVAE_T_RDEC_B,
-       MFVAE_T_RLIN_W, MFVAE_T_RLIN_B };
+       MFVAE_T_RLIN_W, MFVAE_T_RLIN_B, MFVAE_T_ACTENC_W, MFVAE_T_ACTENC_B /* layer 0 / 1 of the ActionEncoder */ };
 typedef struct MfvaeTensorInfo {
   int32_t kind;      /* MFVAE_T_*                         */
   int32_t agent;     /* agent index or -1                 */
@@ -90,7 +94,8 @@ typedef struct MfvaeArenas {
  * obs/next are the agents' observation vectors concatenated in codebook order. */
 typedef struct MfvaeBatch {
   const float* d_obs;      /* [B, S]   fp32                                            */
-  const float* d_act;      /* [B, A]   fp32-coded action index (replay_buffer.py:76)   */
+  const float* d_act;      /* [B, A]   fp32-coded action index (replay_buffer.py:76); continuous_act: [B, sum(action_dim)]
+                              action vectors of all agents concatenated in codebook order                   */
   const float* d_next;     /* [B, S]   target next state   (may be NULL for forward only) */
   const float* d_rew;      /* [B, A]   target rewards      (may be NULL for forward only) */
   const float* d_idx;      /* [B, A]   fp32-coded agent index column, or NULL = codebook order */
@@ -139,6 +144,9 @@ int mfvae_forward(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* s
 int mfvae_loss(MfvaeHandle h, const MfvaeBatch* b, int32_t loss_kind, void* stream);
 /* the reference reads kl_weight / r_weight module globals at call time (model.py:5-6,34,39) */
 int mfvae_set_loss_weights(MfvaeHandle h, float kl_weight, float r_weight);
+/* jax_ver weighting (jax_ver/trainer.py:42-43,64): loss = s_weight * s + r_weight * r + kl_weight * kl with
+ * s_weight = 1 - r_weight, kl_weight = 0.1, r_weight = 0.5.  mfvae_set_loss_weights resets s_weight to 1. */
+int mfvae_set_loss_weights3(MfvaeHandle h, float kl_weight, float r_weight, float s_weight);
 int mfvae_backward(MfvaeHandle h, const MfvaeBatch* b, void* stream);
 /* backward seeded by caller-provided upstream gradients (autograd bridge for losses other than the fused
  * ELBO): d loss / d recon_s [B, ld_s], d loss / d recon_r [B, ld_r], d loss / d latent [A][B][2L]; fp32, any

@@ -14,7 +14,8 @@ PREC_FP32, PREC_BF16 = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 FUSE_AUTO, FUSE_NONE, FUSE_ENCODER, FUSE_LOSS = 0, 1, 2, 4
 LOSS_DEFAULT, LOSS_HUBER, LOSS_MSE, LOSS_JOINT_MSE = 0, 1, 2, 3
-(T_IDX_EMB, T_ENC_W, T_ENC_B, T_ACT_TABLE, T_SDEC_W, T_SDEC_B, T_RDEC_W, T_RDEC_B, T_RLIN_W, T_RLIN_B) = range(10)
+(T_IDX_EMB, T_ENC_W, T_ENC_B, T_ACT_TABLE, T_SDEC_W, T_SDEC_B, T_RDEC_W, T_RDEC_B, T_RLIN_W, T_RLIN_B, T_ACTENC_W,
+ T_ACTENC_B) = range(12)
 
 
 class MfvaeConfig(C.Structure):
@@ -24,7 +25,7 @@ class MfvaeConfig(C.Structure):
                 ("obs_dim", C.POINTER(C.c_int32)), ("n_act", C.POINTER(C.c_int32)),
                 ("kl_weight", C.c_float), ("r_weight", C.c_float), ("huber", C.c_int32),
                 ("precision", C.c_int32), ("engine", C.c_int32), ("optimize_encoders", C.c_int32),
-                ("fusion", C.c_int32)]
+                ("fusion", C.c_int32), ("continuous_act", C.c_int32), ("act_hidden", C.c_int32)]
 
 
 class MfvaeTensorInfo(C.Structure):
@@ -71,6 +72,7 @@ SIGNATURES = {
     "mfvae_forward": (C.c_int, [_vp, C.POINTER(MfvaeBatch), C.POINTER(MfvaeOutputs), _vp]),
     "mfvae_loss": (C.c_int, [_vp, C.POINTER(MfvaeBatch), _i32, _vp]),
     "mfvae_set_loss_weights": (C.c_int, [_vp, _f, _f]),
+    "mfvae_set_loss_weights3": (C.c_int, [_vp, _f, _f, _f]),
     "mfvae_backward": (C.c_int, [_vp, C.POINTER(MfvaeBatch), _vp]),
     "mfvae_backward_ext": (C.c_int, [_vp, C.POINTER(MfvaeBatch), _vp, _i64, _vp, _i64, _vp, _vp]),
     "mfvae_adam_step": (C.c_int, [_vp, _f, _f, _f, _f, _i64, _vp]),

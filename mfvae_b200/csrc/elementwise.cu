@@ -93,6 +93,31 @@ __global__ void __launch_bounds__(kThreads) act_embed_kernel(StageArgs p) {
   }
 }
 
+// continuous-action staging (reference model.py:148: actions[agent].to(device) feeds the ActionEncoder)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) stage_actions_kernel(const float* __restrict__ act, int64_t act_ld,
+                                                                 const int32_t* __restrict__ act_off, const int32_t* __restrict__ act_dim,
+                                                                 T* __restrict__ act0, int A, int64_t B, int Kap) {
+  const int64_t total = static_cast<int64_t>(A) * B * Kap;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % Kap);
+    const int64_t r = i / Kap;
+    const int64_t b = r % B;
+    const int a = static_cast<int>(r / B);
+    act0[i] = from_f<T>(k < act_dim[a] ? __ldg(act + b * act_ld + act_off[a] + k) : 0.f);
+  }
+}
+
+int launch_stage_actions(const float* act, int64_t act_ld, const int32_t* act_off, const int32_t* act_dim, void* act0, int dtype,
+                         int A, int64_t B, int Kap, cudaStream_t s) {
+  const int grid = grid_for(static_cast<int64_t>(A) * B * Kap);
+  if (dtype == kBF16) stage_actions_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(act, act_ld, act_off, act_dim, static_cast<__nv_bfloat16*>(act0), A, B, Kap);
+  else                stage_actions_kernel<float><<<grid, kThreads, 0, s>>>(act, act_ld, act_off, act_dim, static_cast<float*>(act0), A, B, Kap);
+  MFVAE_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_stage(const StageArgs& a, cudaStream_t s, bool do_x0, bool do_act) {
   MFVAE_CHECK(a.x0_ld % 4 == 0 && a.C % 4 == 0 && a.zin_ld % 4 == 0, "stage: widths must be multiples of 4");
   const int64_t t0 = static_cast<int64_t>(a.A) * a.B * (a.x0_ld / 4);
@@ -608,7 +633,7 @@ int launch_philox_normal(float* out, int64_t B, int width, uint64_t seed, uint64
   return 0;
 }
 
-__global__ void __launch_bounds__(kThreads) loss_total_kernel(float* losses, float r_weight, float kl_weight,
+__global__ void __launch_bounds__(kThreads) loss_total_kernel(float* losses, float s_weight, float r_weight, float kl_weight,
                                                               const float* partials, int n_partials, float partial_scale) {
   __shared__ float red[32];
   if (partials) {                         // fixed summation order: the value is reproducible run to run
@@ -617,11 +642,11 @@ __global__ void __launch_bounds__(kThreads) loss_total_kernel(float* losses, flo
     v = block_sum(v, red);
     if (threadIdx.x == 0) losses[1] = v * partial_scale;
   }
-  if (threadIdx.x == 0) losses[0] = losses[1] + r_weight * losses[2] + kl_weight * losses[3];
+  if (threadIdx.x == 0) losses[0] = s_weight * losses[1] + r_weight * losses[2] + kl_weight * losses[3];
 }
-int launch_loss_total(float* losses, float r_weight, float kl_weight, cudaStream_t s, const float* partials, int n_partials,
+int launch_loss_total(float* losses, float s_weight, float r_weight, float kl_weight, cudaStream_t s, const float* partials, int n_partials,
                       float partial_scale) {
-  loss_total_kernel<<<1, kThreads, 0, s>>>(losses, r_weight, kl_weight, partials, n_partials, partial_scale);
+  loss_total_kernel<<<1, kThreads, 0, s>>>(losses, s_weight, r_weight, kl_weight, partials, n_partials, partial_scale);
   MFVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -75,6 +75,10 @@ int launch_act_table_grad(const void* gzin, int dtype, int64_t ld, int col0, con
                           const int32_t* n_act, int A, int C, int64_t B, float* d_table, int64_t table_gs,
                           cudaStream_t s);
 
+// continuous actions: act [B, sum D_a] fp32 -> ACT0[a][b][0..Kap) (zero padded), the ActionEncoder's first operand
+int launch_stage_actions(const float* act, int64_t act_ld, const int32_t* act_off, const int32_t* act_dim, void* act0, int dtype,
+                         int A, int64_t B, int Kap, cudaStream_t s);
+
 int launch_adam(float* p, const float* g, float* m, float* v, __nv_bfloat16* shadow, int64_t n,
                 float lr, float b1, float b2, float eps, int64_t t, cudaStream_t s);
 // dst[b][c] = src[b][c] for c < width (fp32 -> activation dtype); src == nullptr writes zeros
@@ -82,9 +86,9 @@ int launch_cast2d(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, i
 int launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t s);
 int launch_philox_normal(float* out, int64_t B, int width, uint64_t seed, uint64_t step, int64_t sample0,
                          cudaStream_t s);
-// losses[0] = s + r_w * r + kl_w * kl  given losses[1..3]
+// losses[0] = s_w * s + r_w * r + kl_w * kl  given losses[1..3]
 // also sums `n_partials` per-warp partials of the fused output-layer loss into losses[1] (scaled) when partials != nullptr
-int launch_loss_total(float* losses, float r_weight, float kl_weight, cudaStream_t s, const float* partials = nullptr,
+int launch_loss_total(float* losses, float s_weight, float r_weight, float kl_weight, cudaStream_t s, const float* partials = nullptr,
                       int n_partials = 0, float partial_scale = 0.f);
 
 // ---- GEMM (gemm_simt.cu / gemm_tc.cu) --------------------------------------------------------

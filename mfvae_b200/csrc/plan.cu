@@ -39,6 +39,9 @@ struct MfvaeHandle_ {
   int device = 0;
   std::vector<int32_t> obs_dim, n_act, obs_off;
   int A = 0, I = 0, L = 0, C = 0, S = 0, Sp = 0, Ap = 0, Ip = 0, Din = 0, K0p = 0, nact_max = 0;
+  float s_weight = 1.0f;                     // weight of the state reconstruction term (1 in torch_ver; 1 - r_weight in jax_ver)
+  bool cont_act = false; int Hact = 64, Kap = 8, act_total = 0;   // continuous actions: ActionEncoder D_a -> Hact -> C
+  std::vector<int32_t> act_off;
   int ne = 0, nd = 0;                       // number of Linear layers in encoder / decoder
   std::vector<int> encN, encK;              // per encoder layer (K padded)
   std::vector<int> decH;                    // decoder hidden widths
@@ -47,6 +50,7 @@ struct MfvaeHandle_ {
 
   // arena layout
   Span idx_emb, rlW, rlb, sOutW, sOutB, rOutW, rOutB, actT;
+  Span actW1, actB1, actW2, actB2;          // ActionEncoder (continuous actions): [A][Hact][Kap], [A][Hact], [A][C][Hact], [A][C]
   std::vector<Span> decW, decB;             // per hidden layer: rows = 2*H (state rows then reward rows)
   std::vector<Span> encW, encB;             // rows = A*N_l
   int64_t arena_elems = 0, optimized_elems = 0, reg3_begin = 0, reg2_begin = 0, enc_begin = 0;
@@ -54,12 +58,12 @@ struct MfvaeHandle_ {
   MfvaeArenas ar{};
 
   // device constants
-  int32_t* d_meta = nullptr;                // obs_off | obs_dim | n_act
+  int32_t* d_meta = nullptr;                // obs_off | obs_dim | n_act | act_off
 
   // workspace
   char* ws = nullptr; int64_t ws_bytes = 0; int B = 0;
   struct Buf { int64_t off = 0; int64_t ld = 0; int64_t gs = 0; };
-  Buf X0, LAT, ZIN, RS, RR0, RR, DRS, DRR, DRR0, GZIN, DLAT, GX0;
+  Buf X0, LAT, ZIN, RS, RR0, RR, DRS, DRR, DRR0, GZIN, DLAT, GX0, ACT0, HA, DHA;
   std::vector<Buf> XE, DXE, HD, DHD;
   int64_t off_losses = 0, off_scratch = 0;
 
@@ -70,6 +74,7 @@ struct MfvaeHandle_ {
   std::vector<int> g_enc_fwd, g_enc_wg, g_enc_dg, g_dec_fwd, g_dec_wg, g_dec_dg;
   int g_sout_fwd = -1, g_rout_fwd = -1, g_rl_fwd = -1;
   int g_sout_loss = -1;                      // state output layer with the reconstruction loss + its gradient as the epilogue
+  int g_act_fwd1 = -1, g_act_fwd2 = -1, g_act_wg2 = -1, g_act_dg2 = -1, g_act_wg1 = -1;
   int g_sout_wg = -1, g_sout_dg = -1, g_rout_wg = -1, g_rout_dg = -1, g_rl_wg = -1, g_rl_dg = -1;
 
   // side stream for the wgrad / bias-gradient chain of backward, with its fork / join events
@@ -78,6 +83,8 @@ struct MfvaeHandle_ {
   cudaEvent_t join_ev = nullptr;
   // third stream: the reward head (two tiny GEMM chains) and the action-embedding kernels run beside the big layers
   cudaStream_t aux = nullptr;
+  cudaStream_t csum = nullptr;               // fourth stream: the bias column sums (HBM-bound) run beside the wgrad GEMMs
+  std::vector<cudaEvent_t> csum_ev;
   cudaEvent_t aux_fork_ev = nullptr, aux_join_ev = nullptr, aux_fork2_ev = nullptr, aux_join2_ev = nullptr;
   cudaStream_t opt_stream = nullptr;         // overlapped Adam
   cudaEvent_t opt_ev = nullptr, dec_read_ev = nullptr;
@@ -179,9 +186,29 @@ static int build_layout(MfvaeHandle_* h) {
       add_info(h, MFVAE_T_ENC_B, a, l, 1, N, N, h->encB[l].off + static_cast<int64_t>(a) * N);
     }
   }
-  h->actT = {take(cur, static_cast<int64_t>(h->A) * h->nact_max * h->C), h->A * h->nact_max, h->C, h->C};
-  for (int a = 0; a < h->A; ++a)
-    add_info(h, MFVAE_T_ACT_TABLE, a, -1, h->n_act[a], h->C, h->C, h->actT.off + static_cast<int64_t>(a) * h->nact_max * h->C);
+  h->cont_act = c.continuous_act != 0;
+  h->Hact = c.act_hidden > 0 ? c.act_hidden : 64;
+  MFVAE_CHECK(h->Hact % 8 == 0, "act_hidden must be a multiple of 8");
+  h->act_off.resize(h->A); h->act_total = 0;
+  for (int a = 0; a < h->A; ++a) { h->act_off[a] = h->act_total; h->act_total += h->cont_act ? h->n_act[a] : 1; }
+  if (!h->cont_act) {
+    h->actT = {take(cur, static_cast<int64_t>(h->A) * h->nact_max * h->C), h->A * h->nact_max, h->C, h->C};
+    for (int a = 0; a < h->A; ++a)
+      add_info(h, MFVAE_T_ACT_TABLE, a, -1, h->n_act[a], h->C, h->C, h->actT.off + static_cast<int64_t>(a) * h->nact_max * h->C);
+  } else {
+    const int A = h->A, Hh = h->Hact, C = h->C;
+    h->Kap = static_cast<int>(round_up(h->nact_max, 8));          // K of the first layer, zero padded (16-byte TMA rows)
+    h->actW1 = {take(cur, static_cast<int64_t>(A) * Hh * h->Kap), A * Hh, h->Kap, h->Kap};
+    h->actB1 = {take(cur, static_cast<int64_t>(A) * Hh), A, Hh, Hh};
+    h->actW2 = {take(cur, static_cast<int64_t>(A) * C * Hh), A * C, Hh, Hh};
+    h->actB2 = {take(cur, static_cast<int64_t>(A) * C), A, C, C};
+    for (int a = 0; a < A; ++a) {
+      add_info(h, MFVAE_T_ACTENC_W, a, 0, Hh, h->n_act[a], h->Kap, h->actW1.off + static_cast<int64_t>(a) * Hh * h->Kap);
+      add_info(h, MFVAE_T_ACTENC_B, a, 0, 1, Hh, Hh, h->actB1.off + static_cast<int64_t>(a) * Hh);
+      add_info(h, MFVAE_T_ACTENC_W, a, 1, C, Hh, Hh, h->actW2.off + static_cast<int64_t>(a) * C * Hh);
+      add_info(h, MFVAE_T_ACTENC_B, a, 1, 1, C, C, h->actB2.off + static_cast<int64_t>(a) * C);
+    }
+  }
   h->arena_elems = cur;
   h->optimized_elems = c.optimize_encoders ? cur : h->enc_begin;
   return 0;
@@ -216,6 +243,7 @@ static int64_t layout_workspace(MfvaeHandle_* h, int B) {
   h->DLAT = mk(A, 2 * h->L, es, true);
   for (int l = 0; l + 1 < h->ne; ++l) h->DXE.push_back(mk(A, h->encN[l], es, true));
   h->GX0 = mk(A, h->Ip, es, true);
+  if (h->cont_act) { h->ACT0 = mk(A, h->Kap, es, true); h->HA = mk(A, h->Hact, es, true); h->DHA = mk(A, h->Hact, es, true); }
   h->off_losses = alloc(64 * sizeof(float));
   h->off_scratch = alloc(3 * 4096 * sizeof(float));
   return cur;
@@ -300,6 +328,21 @@ static int build_ops(MfvaeHandle_* h) {
       h->g_enc_dg.push_back(dgrad(A, K, N, buf(D), D.gs, D.ld, wptr(h->encW[l].off), static_cast<int64_t>(N) * K, K,
                                   buf(dx), dx.gs, dx.ld, buf(in), in.gs, in.ld));
     }
+  }
+  // ---- ActionEncoder (continuous actions, G = A): D_a -> Hact (ReLU) -> C, written straight into its ZIN columns ----
+  if (h->cont_act) {
+    const int Hh = h->Hact, C = h->C, Kap = h->Kap;
+    char* zact = ws + h->ZIN.off + static_cast<int64_t>(A) * h->L * es;       // column A*L of ZIN: agent a at + a*C
+    char* gzact = ws + h->GZIN.off + static_cast<int64_t>(A) * h->L * es;
+    h->g_act_fwd1 = fwd(A, B, Hh, Kap, buf(h->ACT0), h->ACT0.gs, h->ACT0.ld, wptr(h->actW1.off), static_cast<int64_t>(Hh) * Kap, Kap,
+                        buf(h->HA), h->HA.gs, h->HA.ld, dt, P + h->actB1.off, Hh, true);
+    h->g_act_fwd2 = fwd(A, B, C, Hh, buf(h->HA), h->HA.gs, h->HA.ld, wptr(h->actW2.off), static_cast<int64_t>(C) * Hh, Hh,
+                        zact, C, h->ZIN.ld, dt, P + h->actB2.off, C, false);
+    h->g_act_wg2 = wgrad(A, C, Hh, gzact, C, h->GZIN.ld, buf(h->HA), h->HA.gs, h->HA.ld, h->actW2.off, static_cast<int64_t>(C) * Hh, Hh);
+    h->g_act_dg2 = dgrad(A, Hh, C, gzact, C, h->GZIN.ld, wptr(h->actW2.off), static_cast<int64_t>(C) * Hh, Hh,
+                         buf(h->DHA), h->DHA.gs, h->DHA.ld, buf(h->HA), h->HA.gs, h->HA.ld);
+    h->g_act_wg1 = wgrad(A, Hh, Kap, buf(h->DHA), h->DHA.gs, h->DHA.ld, buf(h->ACT0), h->ACT0.gs, h->ACT0.ld,
+                         h->actW1.off, static_cast<int64_t>(Hh) * Kap, Kap);
   }
   // ---- decoders: hidden layers (layer 0 fused over both decoders, others G = 2 over column halves) ----
   const int nh = h->cfg.n_dec_hidden;
@@ -391,11 +434,20 @@ static float* scratch_ptr(MfvaeHandle_* h, int i) { return reinterpret_cast<floa
 static bool use_aux(const MfvaeHandle_* h) { return h->aux != nullptr && !h->profiling; }
 
 // action-embedding half of the decoder input: independent of the encoders, so it runs beside them on the aux stream
+static int act_embed_on(MfvaeHandle_* h, const StageArgs& st, cudaStream_t q) {
+  if (!h->cont_act) return launch_stage(st, q, false, true);
+  // ActionEncoder MLP (reference model.py:148)
+  MFVAE_TRY(launch_stage_actions(st.act, h->act_total, h->d_meta + 3 * h->A, h->d_meta + 2 * h->A, h->ws + h->ACT0.off, h->dtype,
+                                 h->A, h->B, h->Kap, q));
+  MFVAE_TRY(run_gemm(h, h->g_act_fwd1, q));
+  return run_gemm(h, h->g_act_fwd2, q);
+}
+
 static int do_forward_act_embed(MfvaeHandle_* h, const StageArgs& st, cudaStream_t s) {
-  if (!use_aux(h)) return launch_stage(st, s, false, true);
+  if (!use_aux(h)) return act_embed_on(h, st, s);
   MFVAE_CUDA(cudaEventRecord(h->aux_fork_ev, s));          // orders it after whatever last read ZIN on the caller's stream
   MFVAE_CUDA(cudaStreamWaitEvent(h->aux, h->aux_fork_ev, 0));
-  MFVAE_TRY(launch_stage(st, h->aux, false, true));
+  MFVAE_TRY(act_embed_on(h, st, h->aux));
   MFVAE_CUDA(cudaEventRecord(h->aux_join_ev, h->aux));
   return 0;
 }
@@ -415,7 +467,8 @@ static int do_forward_decoders(MfvaeHandle_* h, cudaStream_t s, const MfvaeBatch
   }
   if (loss_batch) {
     const double cs = static_cast<double>(loss_batch->batch_global) * h->S;
-    MFVAE_TRY(gemm_tc_set_loss(h->tc[h->g_sout_loss], loss_batch->d_next, h->S, static_cast<float>(1.0 / cs), huber, scratch_ptr(h, 1)));
+    MFVAE_TRY(gemm_tc_set_loss(h->tc[h->g_sout_loss], loss_batch->d_next, h->S, static_cast<float>(static_cast<double>(h->s_weight) / cs), huber,
+                               scratch_ptr(h, 1)));
     MFVAE_TRY(run_gemm(h, h->g_sout_loss, s));
   } else {
     MFVAE_TRY(run_gemm(h, h->g_sout_fwd, s));
@@ -433,9 +486,9 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
   MFVAE_TRY(check_ready(h, b));
   const MfvaeBatch* lb = fuse_loss ? b : nullptr;
   StageArgs st{};
-  st.obs = b->d_obs; st.obs_ld = h->S; st.act = b->d_act; st.act_ld = h->A; st.idx = b->d_idx;
+  st.obs = b->d_obs; st.obs_ld = h->S; st.act = b->d_act; st.act_ld = h->cont_act ? h->act_total : h->A; st.idx = b->d_idx;
   st.idx_emb = h->ar.d_param + h->idx_emb.off;
-  st.act_table = h->ar.d_param + h->actT.off; st.act_table_gs = static_cast<int64_t>(h->nact_max) * h->C; st.n_act_max = h->nact_max;
+  st.act_table = h->cont_act ? nullptr : h->ar.d_param + h->actT.off; st.act_table_gs = static_cast<int64_t>(h->nact_max) * h->C; st.n_act_max = h->nact_max;
   st.obs_off = h->d_meta; st.obs_dim = h->d_meta + h->A; st.n_act = h->d_meta + 2 * h->A;
   st.x0 = h->ws + h->X0.off; st.x0_ld = static_cast<int>(h->X0.ld); st.x0_gs = h->X0.gs;
   st.zin = h->ws + h->ZIN.off; st.zin_ld = static_cast<int>(h->ZIN.ld);
@@ -487,7 +540,8 @@ static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStre
   const double cr = joint_mse ? Bg * (h->S + h->A) : Bg * h->A;
   const float rw = joint_mse ? 1.0f : h->cfg.r_weight;
   a.huber = joint_mse ? 0 : use_huber;
-  a.grad_scale = static_cast<float>(1.0 / cs); a.loss_scale = static_cast<float>(1.0 / cs);
+  const float sw = joint_mse ? 1.0f : h->s_weight;
+  a.grad_scale = static_cast<float>(static_cast<double>(sw) / cs); a.loss_scale = static_cast<float>(1.0 / cs);
   a.loss_out = losses_ptr(h) + 1; a.scratch = scratch_ptr(h, 1);
   if (!state_fused) MFVAE_TRY(launch_recon_loss(a, s));
   a.recon = reinterpret_cast<const float*>(h->ws + h->RR.off); a.recon_ld = h->RR.ld;
@@ -497,10 +551,10 @@ static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStre
   a.loss_out = losses_ptr(h) + 2; a.scratch = scratch_ptr(h, 2);
   MFVAE_TRY(launch_recon_loss(a, s));
   if (state_fused)
-    MFVAE_TRY(launch_loss_total(losses_ptr(h), rw, h->cfg.kl_weight, s, scratch_ptr(h, 1), gemm_tc_loss_partials(h->tc[h->g_sout_loss]),
+    MFVAE_TRY(launch_loss_total(losses_ptr(h), sw, rw, h->cfg.kl_weight, s, scratch_ptr(h, 1), gemm_tc_loss_partials(h->tc[h->g_sout_loss]),
                                 static_cast<float>(1.0 / cs)));
   else
-    MFVAE_TRY(launch_loss_total(losses_ptr(h), rw, h->cfg.kl_weight, s));
+    MFVAE_TRY(launch_loss_total(losses_ptr(h), sw, rw, h->cfg.kl_weight, s));
   return 0;
 }
 
@@ -514,14 +568,26 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
   float* G = h->ar.d_grad;
   char* ws = h->ws;
   const bool overlap = h->side != nullptr && !h->profiling;     // profiling wants serialised, undisturbed durations
-  cudaStream_t w = overlap ? h->side : s;                       // stream of the wgrad / colsum chain
+  cudaStream_t w = overlap ? h->side : s;                       // stream of the wgrad chain
+  cudaStream_t cs = (overlap && h->csum) ? h->csum : w;         // stream of the bias column sums
   size_t ev_i = 0;
   auto fork = [&]() -> int {
     if (!overlap) return 0;
     MFVAE_CHECK(ev_i < h->fork_ev.size(), "fork event pool exhausted");
     MFVAE_CUDA(cudaEventRecord(h->fork_ev[ev_i], s));
     MFVAE_CUDA(cudaStreamWaitEvent(w, h->fork_ev[ev_i], 0));
+    if (cs != w) MFVAE_CUDA(cudaStreamWaitEvent(cs, h->fork_ev[ev_i], 0));
     ++ev_i;
+    return 0;
+  };
+  // the column sums of a gradient bucket finish on `cs`: fold them into `w` before the bucket's event is recorded there
+  size_t cs_i = 0;
+  auto csum_into_w = [&]() -> int {
+    if (cs == w) return 0;
+    MFVAE_CHECK(cs_i < h->csum_ev.size(), "column-sum event pool exhausted");
+    MFVAE_CUDA(cudaEventRecord(h->csum_ev[cs_i], cs));
+    MFVAE_CUDA(cudaStreamWaitEvent(w, h->csum_ev[cs_i], 0));
+    ++cs_i;
     return 0;
   };
   // optimizer.zero_grad(): split-K wgrads and bias column sums accumulate with fp32 atomics.  The two largest weight
@@ -549,7 +615,7 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
   }
   // output layers + reward_linear
   MFVAE_TRY(run_gemm(h, h->g_sout_wg, w));
-  MFVAE_TRY(launch_colsum(ws + h->DRS.off, dt, 1, h->B, h->S, h->DRS.ld, 0, G + h->sOutB.off, 0, w));
+  MFVAE_TRY(launch_colsum(ws + h->DRS.off, dt, 1, h->B, h->S, h->DRS.ld, 0, G + h->sOutB.off, 0, cs));
   MFVAE_TRY(run_gemm(h, h->g_sout_dg, s));
   MFVAE_TRY(run_gemm(h, h->g_rl_dg, r));
   MFVAE_TRY(run_gemm(h, h->g_rout_dg, r));
@@ -566,16 +632,18 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
     MFVAE_CUDA(cudaEventRecord(h->aux_join2_ev, h->aux));
     MFVAE_CUDA(cudaStreamWaitEvent(w, h->aux_join2_ev, 0));
   }
+  MFVAE_TRY(csum_into_w());
   MFVAE_CUDA(cudaEventRecord(h->buckets[0].ev, w));
   // decoder hidden layers, last to first
   for (int l = nh - 1; l >= 0; --l) {
     MFVAE_TRY(fork());                                          // D_l (both decoder halves) ready
     MFVAE_TRY(run_gemm(h, h->g_dec_wg[l], w));
-    MFVAE_TRY(launch_colsum(ws + h->DHD[l].off, dt, 1, h->B, 2 * h->decH[l], h->DHD[l].ld, 0, G + h->decB[l].off, 0, w));
-    if (l == 1) MFVAE_CUDA(cudaEventRecord(h->buckets[1].ev, w));
+    MFVAE_TRY(launch_colsum(ws + h->DHD[l].off, dt, 1, h->B, 2 * h->decH[l], h->DHD[l].ld, 0, G + h->decB[l].off, 0, cs));
+    if (l == 1) { MFVAE_TRY(csum_into_w()); MFVAE_CUDA(cudaEventRecord(h->buckets[1].ev, w)); }
     MFVAE_TRY(run_gemm(h, h->g_dec_dg[l], s));
   }
   if (nh == 1) MFVAE_CUDA(cudaEventRecord(h->buckets[1].ev, w));
+  MFVAE_TRY(csum_into_w());
   MFVAE_CUDA(cudaEventRecord(h->buckets[2].ev, w));
   if (h->dec_read_ev) MFVAE_CUDA(cudaEventRecord(h->dec_read_ev, s));   // last reader of the decoder weights (dgrad layer 0) is queued
   // action tables (model.py:121: unregistered; gradients still flow)
@@ -585,8 +653,18 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
     MFVAE_CUDA(cudaStreamWaitEvent(h->aux, h->aux_fork2_ev, 0));
     at = h->aux;
   }
-  MFVAE_TRY(launch_act_table_grad(ws + h->GZIN.off, dt, h->GZIN.ld, A * h->L, b->d_act, A, h->d_meta + 2 * A, A, h->C, h->B,
-                                  G + h->actT.off, static_cast<int64_t>(h->nact_max) * h->C, at));
+  if (!h->cont_act) {
+    MFVAE_TRY(launch_act_table_grad(ws + h->GZIN.off, dt, h->GZIN.ld, A * h->L, b->d_act, A, h->d_meta + 2 * A, A, h->C, h->B,
+                                    G + h->actT.off, static_cast<int64_t>(h->nact_max) * h->C, at));
+  } else {   // ActionEncoder backward: D = the action columns of d ZIN
+    const int64_t es = dtype_size(dt);
+    const char* gzact = ws + h->GZIN.off + static_cast<int64_t>(A) * h->L * es;
+    MFVAE_TRY(run_gemm(h, h->g_act_wg2, at));
+    MFVAE_TRY(launch_colsum(gzact, dt, A, h->B, h->C, h->GZIN.ld, h->C, G + h->actB2.off, h->C, at));
+    MFVAE_TRY(run_gemm(h, h->g_act_dg2, at));
+    MFVAE_TRY(run_gemm(h, h->g_act_wg1, at));
+    MFVAE_TRY(launch_colsum(ws + h->DHA.off, dt, A, h->B, h->Hact, h->DHA.ld, h->DHA.gs, G + h->actB1.off, h->Hact, at));
+  }
   if (auxo) MFVAE_CUDA(cudaEventRecord(h->aux_join_ev, h->aux));
   // reparameterization + KL backward
   ReparamBwdArgs rb{};
@@ -604,7 +682,7 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
     const MfvaeHandle_::Buf& D = (l + 1 == h->ne) ? h->DLAT : h->DXE[l];
     MFVAE_TRY(fork());
     MFVAE_TRY(run_gemm(h, h->g_enc_wg[l], w));
-    MFVAE_TRY(launch_colsum(ws + D.off, dt, A, h->B, h->encN[l], D.ld, D.gs, G + h->encB[l].off, h->encN[l], w));
+    MFVAE_TRY(launch_colsum(ws + D.off, dt, A, h->B, h->encN[l], D.ld, D.gs, G + h->encB[l].off, h->encN[l], cs));
     MFVAE_TRY(run_gemm(h, h->g_enc_dg[l], s));
   }
   // id embedding (model.py:113,142)
@@ -613,6 +691,7 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
   else
     MFVAE_TRY(launch_colsum(ws + h->GX0.off, dt, A, h->B, h->I, h->GX0.ld, h->GX0.gs, G + h->idx_emb.off, h->I, s));
   if (overlap) {                                               // join
+    MFVAE_TRY(csum_into_w());
     MFVAE_CUDA(cudaEventRecord(h->join_ev, w));
     MFVAE_CUDA(cudaStreamWaitEvent(s, h->join_ev, 0));
     if (auxo) MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join_ev, 0));
@@ -667,6 +746,8 @@ int mfvae_create(const MfvaeConfig* cfg, int device, MfvaeHandle* out) {
   }
   cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming);
   if (cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess) h->aux = nullptr;
+  if (cudaStreamCreateWithFlags(&h->csum, cudaStreamNonBlocking) != cudaSuccess) h->csum = nullptr;
+  for (int i = 0; i < 6; ++i) { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); h->csum_ev.push_back(e); }
   cudaEventCreateWithFlags(&h->aux_fork_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->aux_join_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->aux_fork2_ev, cudaEventDisableTiming);
@@ -678,6 +759,7 @@ int mfvae_create(const MfvaeConfig* cfg, int device, MfvaeHandle* out) {
   meta.insert(meta.end(), h->obs_off.begin(), h->obs_off.end());
   meta.insert(meta.end(), h->obs_dim.begin(), h->obs_dim.end());
   meta.insert(meta.end(), h->n_act.begin(), h->n_act.end());
+  meta.insert(meta.end(), h->act_off.begin(), h->act_off.end());
   if (cudaMalloc(&h->d_meta, meta.size() * sizeof(int32_t)) != cudaSuccess ||
       cudaMemcpy(h->d_meta, meta.data(), meta.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
     delete h; MFVAE_FAIL("cudaMalloc / cudaMemcpy of the agent table failed");
@@ -695,6 +777,8 @@ int mfvae_destroy(MfvaeHandle h) {
   if (h->join_ev) cudaEventDestroy(h->join_ev);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->aux) cudaStreamDestroy(h->aux);
+  if (h->csum) cudaStreamDestroy(h->csum);
+  for (auto e : h->csum_ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {h->aux_fork_ev, h->aux_join_ev, h->aux_fork2_ev, h->aux_join2_ev}) if (e) cudaEventDestroy(e);
   if (h->opt_ev) cudaEventDestroy(h->opt_ev);
   if (h->dec_read_ev) cudaEventDestroy(h->dec_read_ev);
@@ -766,7 +850,12 @@ int mfvae_loss(MfvaeHandle h, const MfvaeBatch* b, int32_t loss_kind, void* stre
 }
 int mfvae_set_loss_weights(MfvaeHandle h, float kl_weight, float r_weight) {
   MFVAE_CHECK(h, "null handle");
-  h->cfg.kl_weight = kl_weight; h->cfg.r_weight = r_weight;
+  h->cfg.kl_weight = kl_weight; h->cfg.r_weight = r_weight; h->s_weight = 1.0f;
+  return 0;
+}
+int mfvae_set_loss_weights3(MfvaeHandle h, float kl_weight, float r_weight, float s_weight) {
+  MFVAE_CHECK(h, "null handle");
+  h->cfg.kl_weight = kl_weight; h->cfg.r_weight = r_weight; h->s_weight = s_weight;
   return 0;
 }
 int mfvae_backward(MfvaeHandle h, const MfvaeBatch* b, void* stream) {

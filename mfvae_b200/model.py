@@ -88,7 +88,8 @@ class PackedBatch:
     (reference trainer.py:7-45) produces, without the per-agent dict indirection.
 
     obs  [B, S] fp32   observations of all agents concatenated in codebook order
-    act  [B, A] fp32   float-coded discrete action per agent (replay_buffer.py:76)
+    act  [B, A] fp32   float-coded discrete action per agent (replay_buffer.py:76); continuous actions:
+                       [B, sum(action_dim)] action vectors concatenated in codebook order
     next [B, S] fp32   next observations (= ``next_states`` target)      (optional)
     rew  [B, A] fp32   rewards (= ``rewards`` target)                     (optional)
     idx  [B, A] fp32   agent-index column of ``idx_state`` or None = codebook order
@@ -199,8 +200,6 @@ class MAVAE(nn.Module):
                  include_dead_decoder: bool = True, seed: int = 0x5EED, huber: bool = True,
                  fusion: str = "auto"):
         super().__init__()
-        if not descrete_act:
-            raise NotImplementedError("continuous-action ActionEncoder path (model.py:123,148) is not built yet")
         self.obs_dim = obs_dim
         self.act_dim = action_dim
         self.feature = obs_features
@@ -236,6 +235,8 @@ class MAVAE(nn.Module):
         cfg.precision = {"fp32": L.PREC_FP32, "bf16": L.PREC_BF16}[precision]
         cfg.engine = {"auto": L.ENGINE_AUTO, "simt": L.ENGINE_SIMT, "tcgen05": L.ENGINE_TCGEN05}[engine]
         cfg.optimize_encoders = int(self.optimize_encoders)
+        cfg.continuous_act = 0 if descrete_act else 1
+        cfg.act_hidden = ActionEncoder.HIDDEN[0]
         cfg.fusion = {"auto": L.FUSE_AUTO, "none": L.FUSE_NONE, "encoder": L.FUSE_ENCODER, "loss": L.FUSE_LOSS,
                       "encoder+loss": L.FUSE_ENCODER | L.FUSE_LOSS}[fusion]
         self._cfg = cfg
@@ -322,10 +323,14 @@ class MAVAE(nn.Module):
         self.action_encoder = {}
         for ai, a in enumerate(self.agents):
             self.encoders[a] = self._arena_mlp(Encoder, [(by[(L.T_ENC_W, ai, l)], by[(L.T_ENC_B, ai, l)]) for l in range(ne)])
-            t = by[(L.T_ACT_TABLE, ai, -1)]
-            emb = nn.Embedding(t.rows, t.cols, device="meta")
-            emb.weight = self._param(t)
-            self.action_encoder[a] = emb
+            if self.descrete_act:
+                t = by[(L.T_ACT_TABLE, ai, -1)]
+                emb = nn.Embedding(t.rows, t.cols, device="meta")
+                emb.weight = self._param(t)
+                self.action_encoder[a] = emb
+            else:       # model.py:123: ActionEncoder(act_dim, action_features), arena-backed like the encoders
+                self.action_encoder[a] = self._arena_mlp(ActionEncoder, [(by[(L.T_ACTENC_W, ai, l)], by[(L.T_ACTENC_B, ai, l)])
+                                                                         for l in range(2)])
         S = sum(int(self.obs_dim[a]) for a in self.agents)
         din = (self.feature + self.action_features) * A
         if include_dead_decoder:   # model.py:127 — constructed, registered, never called
@@ -351,7 +356,12 @@ class MAVAE(nn.Module):
             for mod in self.encoders[a].net:
                 if isinstance(mod, nn.Linear):
                     init_linear(mod)
-            nn.init.normal_(self.action_encoder[a].weight)
+            if self.descrete_act:
+                nn.init.normal_(self.action_encoder[a].weight)
+            else:
+                for mod in self.action_encoder[a].net:
+                    if isinstance(mod, nn.Linear):
+                        init_linear(mod)
         for dec in (self.state_decoder, self.reward_decoder):
             for mod in dec.net:
                 if isinstance(mod, nn.Linear):
@@ -365,7 +375,8 @@ class MAVAE(nn.Module):
         for a in self.agents:
             for n, p in self.encoders[a].named_parameters():
                 out[f"encoders.{a}.{n}"] = p
-            out[f"action_encoder.{a}.weight"] = self.action_encoder[a].weight
+            for n, p in self.action_encoder[a].named_parameters():     # Embedding: "weight"; ActionEncoder: "net.0.weight", ...
+                out[f"action_encoder.{a}.{n}"] = p
         for pre in ("state_decoder", "reward_decoder", "reward_linear"):
             for n, p in getattr(self, pre).named_parameters():
                 out[f"{pre}.{n}"] = p
@@ -450,7 +461,10 @@ class MAVAE(nn.Module):
         cols = [_f32c(idx_state[a], dev) for a in keys]
         obs = torch.cat([c[:, 1:] for c in cols], dim=1)
         idx = torch.stack([c[:, 0] for c in cols], dim=1).contiguous()
-        act = torch.cat([_f32c(actions[a], dev).reshape(-1, 1) for a in keys], dim=1)
+        if self.descrete_act:
+            act = torch.cat([_f32c(actions[a], dev).reshape(-1, 1) for a in keys], dim=1)
+        else:       # continuous: [B, act_dim_a] vectors, concatenated in agent order
+            act = torch.cat([_f32c(actions[a], dev).reshape(cols[0].shape[0], -1) for a in keys], dim=1).contiguous()
         if eps is not None:
             eps = _f32c(eps, dev)
         return PackedBatch(obs, act, idx=idx, eps=eps)
@@ -489,13 +503,24 @@ class MAVAE(nn.Module):
         return recon_s, recon_r, mu_all, lv_all
 
     # ------------------------------------------------------------------ loss / backward / optimizer
-    def _fused_loss(self, s_hat, r_hat, kind):
+    def _set_weights(self, weights=None):
+        """(kl_weight, r_weight[, s_weight]); None = this module's globals, read at call time like the reference
+        (model.py:5-6,34,39), with the state term weighted 1."""
+        lib = L.lib()
+        if weights is None:
+            L.check(lib.mfvae_set_loss_weights(self._h, kl_weight, r_weight))
+        else:
+            kw, rw = float(weights[0]), float(weights[1])
+            sw = float(weights[2]) if len(weights) > 2 else 1.0
+            L.check(lib.mfvae_set_loss_weights3(self._h, kw, rw, sw))
+
+    def _fused_loss(self, s_hat, r_hat, kind, weights=None):
         lib = L.lib()
         pb = self._cur
         pb.next = _f32c(s_hat, self._tdev)
         pb.rew = _f32c(r_hat, self._tdev)
         self._cb.d_next, self._cb.d_rew = pb.next.data_ptr(), pb.rew.data_ptr()
-        L.check(lib.mfvae_set_loss_weights(self._h, kl_weight, r_weight))
+        self._set_weights(weights)
         L.check(lib.mfvae_loss(self._h, C.byref(self._cb), kind, self._stream()))
         return _FusedLossFn.apply(self._anchor, self, self._losses)
 
@@ -575,13 +600,35 @@ class MAVAE(nn.Module):
         fn = L.lib().mfvae_adam_step_overlapped if overlapped else L.lib().mfvae_adam_step
         L.check(fn(self._h, float(lr), float(betas[0]), float(betas[1]), float(eps), self._adam_t, self._stream()))
 
-    def train_step(self, pb: PackedBatch, lr: float, betas=(0.9, 0.999), eps=1e-8):
-        """Fast path: forward + fused ELBO + backward (+ all-reduce) + Adam, no autograd graph.
-        Returns the device tensor [loss, s_loss, r_loss, kl_loss]."""
+    @torch.no_grad()
+    def test_step(self, pb: PackedBatch, loss_weights=None):
+        """Forward + ELBO without backward / update (jax_ver/trainer.py:86-90 ``test_step``; the torch driver has no
+        evaluation loop).  Returns the device tensor [loss, s_loss, r_loss, kl_loss]; the Philox step is not advanced."""
         self._require_gpu()
         lib = L.lib()
         self._bind(pb.batch)
         self._sync_shadow()
+        self._serial += 1
+        self._cur, self._cb = pb, self._cbatch(pb)
+        out = L.MfvaeOutputs()
+        L.check(lib.mfvae_forward(self._h, C.byref(self._cb), C.byref(out), self._stream()))
+        self._set_weights(loss_weights)
+        L.check(lib.mfvae_loss(self._h, C.byref(self._cb), L.LOSS_DEFAULT, self._stream()))
+        self._losses = self._ws_view(out.d_losses, 1, 4, 4)[0]
+        if self.data_parallel:
+            import torch.distributed as dist
+            dist.all_reduce(self._losses, group=self._pg)
+        return self._losses
+
+    def train_step(self, pb: PackedBatch, lr: float, betas=(0.9, 0.999), eps=1e-8, loss_weights=None):
+        """Fast path: forward + fused ELBO + backward (+ all-reduce) + Adam, no autograd graph.
+        Returns the device tensor [loss, s_loss, r_loss, kl_loss].  ``loss_weights`` = (kl_weight, r_weight[, s_weight])
+        overrides the module globals (e.g. the jax_ver weighting (0.1, 0.5, 0.5))."""
+        self._require_gpu()
+        lib = L.lib()
+        self._bind(pb.batch)
+        self._sync_shadow()
+        self._set_weights(loss_weights)
         self._serial += 1
         self._cur, self._cb = pb, self._cbatch(pb)
         out = L.MfvaeOutputs()

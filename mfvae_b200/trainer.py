@@ -33,27 +33,36 @@ def _layout(transition, codebook):
     return agents, B, dims, int(sum(dims)), len(agents)
 
 
-def _split_flat(flat, B, S, A):
-    """Four dense matrices [obs | act | next | rew] carved out of one flat buffer of B * (2S + 2A) floats."""
-    o0, o1, o2 = B * S, B * (S + A), B * (2 * S + A)
-    return (flat[:o0].reshape(B, S), flat[o0:o1].reshape(B, A), flat[o1:o2].reshape(B, S), flat[o2:].reshape(B, A))
+def _act_dims(transition, agents):
+    """Action columns per agent: 1 for a float-coded discrete action, act_dim for a continuous action vector."""
+    return [int(np.prod(transition[a + "_actions"].shape[1:])) or 1 for a in agents]
+
+
+def _split_flat(flat, B, S, A, W=None):
+    """Four dense matrices [obs | act | next | rew] carved out of one flat buffer of B * (2S + W + A) floats; W = total
+    action columns (= A for discrete actions)."""
+    W = A if W is None else W
+    o0, o1, o2 = B * S, B * (S + W), B * (2 * S + W)
+    return (flat[:o0].reshape(B, S), flat[o0:o1].reshape(B, W), flat[o1:o2].reshape(B, S), flat[o2:o2 + B * A].reshape(B, A))
 
 
 def _pack_numpy(transition: Dict[str, np.ndarray], codebook: Dict[str, int], flat: Optional[np.ndarray] = None):
     """Single pass over the sampled dict into one flat float32 buffer holding obs[B,S], act[B,A], next[B,S],
     rew[B,A] back to back, agents in codebook order (no quadratic re-concatenation as in trainer.py:23-30)."""
     agents, B, dims, S, A = _layout(transition, codebook)
+    adims = _act_dims(transition, agents)
+    W = int(sum(adims))
     if flat is None:
-        flat = np.empty(B * (2 * S + 2 * A), dtype=np.float32)
-    obs, act, nxt, rew = _split_flat(flat, B, S, A)
-    o = 0
+        flat = np.empty(B * (2 * S + W + A), dtype=np.float32)
+    obs, act, nxt, rew = _split_flat(flat, B, S, A, W)
+    o = ao = 0
     for i, a in enumerate(agents):
         d = dims[i]
         obs[:, o:o + d] = transition[a + "_observations"]
         nxt[:, o:o + d] = transition[a + "_next_observations"]
-        act[:, i] = transition[a + "_actions"].reshape(B)
+        act[:, ao:ao + adims[i]] = transition[a + "_actions"].reshape(B, adims[i])
         rew[:, i] = transition[a + "_rewards"].reshape(B)
-        o += d
+        o += d; ao += adims[i]
     return flat, (obs, act, nxt, rew), dims
 
 
@@ -62,17 +71,18 @@ def create_dataset(transition, codebook):
     two dicts of CPU tensors ([B, 1 + O_a] with the codebook index in column 0; [B, 1]) and three CPU tensors
     ([B, S + A], [B, S], [B, A])."""
     _, (obs, act, nxt, rew), dims = _pack_numpy(transition, codebook)
+    adims = _act_dims(transition, list(codebook.keys()))
     B = obs.shape[0]
     idx_state_all, action_all = {}, {}
-    o = 0
+    o = ao = 0
     for i, (agent_id, num) in enumerate(codebook.items()):
         d = dims[i]
         block = np.empty((B, d + 1), dtype=obs.dtype)
         block[:, 0] = num
         block[:, 1:] = obs[:, o:o + d]
         idx_state_all[agent_id] = torch.from_numpy(block)
-        action_all[agent_id] = torch.from_numpy(np.ascontiguousarray(act[:, i:i + 1]))
-        o += d
+        action_all[agent_id] = torch.from_numpy(np.ascontiguousarray(act[:, ao:ao + adims[i]]))
+        o += d; ao += adims[i]
     joint = np.concatenate((nxt, rew), axis=1)
     return idx_state_all, action_all, torch.from_numpy(joint), torch.from_numpy(nxt), torch.from_numpy(rew)
 
@@ -92,8 +102,9 @@ class HostStager:
         self.h2d_bytes = 0
 
     def stage(self, transition, codebook, sample0=0, batch_global=None) -> PackedBatch:
-        _, B, _, S, A = _layout(transition, codebook)
-        n = B * (2 * S + 2 * A)
+        agents, B, _, S, A = _layout(transition, codebook)
+        W = int(sum(_act_dims(transition, agents)))
+        n = B * (2 * S + W + A)
         k = self._i
         self._i = (k + 1) % self.depth
         cuda = self.device.type == "cuda"
@@ -108,7 +119,7 @@ class HostStager:
         if cuda:
             self._ev[k] = torch.cuda.Event()
             self._ev[k].record()
-        obs, act, nxt, rew = _split_flat(self._dev[k], B, S, A)
+        obs, act, nxt, rew = _split_flat(self._dev[k], B, S, A, W)
         return PackedBatch(obs, act, nxt, rew, sample0=sample0, batch_global=batch_global)
 
 

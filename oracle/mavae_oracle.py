@@ -55,6 +55,9 @@ class Spec:
     enc_hidden: Sequence[int] = (64, 64, 256)              # torch_ver/model.py:46
     dec_hidden: Sequence[int] = (1024, 256, 64, 256, 1024)  # torch_ver/model.py:87
     include_dead_decoder: bool = False   # the never-called ``decoder`` of model.py:127
+    discrete_act: bool = True            # DESCRETE_ACT torch_ver/main.py:33; False -> ActionEncoder MLP (model.py:60-74,123,148)
+    act_dim: Optional[Dict[str, int]] = None     # continuous action width per agent (used when discrete_act is False)
+    act_hidden: Sequence[int] = (64,)            # ActionEncoder.HIDDEN torch_ver/model.py:63
 
     @property
     def n_agents(self) -> int:
@@ -101,6 +104,10 @@ def layer_dims(spec: Spec) -> Dict[str, List[Tuple[int, int]]]:
     for a in spec.agents:
         widths = [spec.idx_features + spec.obs_dim[a], *spec.enc_hidden, 2 * spec.latent]
         out[f"encoders.{a}"] = [(widths[i + 1], widths[i]) for i in range(len(widths) - 1)]
+    if not spec.discrete_act:
+        for a in spec.agents:
+            widths = [spec.act_dim[a], *spec.act_hidden, spec.act_features]
+            out[f"action_encoder.{a}"] = [(widths[i + 1], widths[i]) for i in range(len(widths) - 1)]
     for name, od in (("state_decoder", spec.state_dim), ("reward_decoder", spec.n_agents),
                      ("decoder", spec.state_dim + spec.n_agents)):
         if name == "decoder" and not spec.include_dead_decoder:
@@ -128,8 +135,9 @@ def init_params(spec: Spec, seed: int = 0, dtype=torch.float32) -> Dict[str, tor
             bound = 1.0 / math.sqrt(i)
             put(wn, rng.uniform(-bound, bound, size=(o, i)))
             put(bn, rng.uniform(-bound, bound, size=(o,)))
-    for a in spec.agents:
-        put(f"action_encoder.{a}.weight", rng.standard_normal((spec.n_act[a], spec.act_features)))
+    if spec.discrete_act:
+        for a in spec.agents:
+            put(f"action_encoder.{a}.weight", rng.standard_normal((spec.n_act[a], spec.act_features)))
     A = spec.n_agents
     put("reward_linear.weight", np.ones((A, A)))
     put("reward_linear.bias", np.zeros((A,)))
@@ -161,7 +169,10 @@ def synth_transition(spec: Spec, batch: int, seed: int = 0, reward_scale: float 
         o = spec.obs_dim[a]
         t[f"{a}_observations"] = rng.standard_normal((batch, o)).astype(np.float32)
         t[f"{a}_next_observations"] = rng.standard_normal((batch, o)).astype(np.float32)
-        t[f"{a}_actions"] = rng.integers(0, spec.n_act[a], size=(batch, 1)).astype(np.float32)
+        if spec.discrete_act:
+            t[f"{a}_actions"] = rng.integers(0, spec.n_act[a], size=(batch, 1)).astype(np.float32)
+        else:       # MPE continuous actions live in [0, 1]
+            t[f"{a}_actions"] = rng.uniform(0.0, 1.0, size=(batch, spec.act_dim[a])).astype(np.float32)
         t[f"{a}_rewards"] = (reward_scale * rng.standard_normal((batch, 1))).astype(np.float32)
     return t
 
@@ -233,8 +244,11 @@ def forward(P: Dict[str, torch.Tensor], spec: Spec, idx_state: Dict[str, torch.T
         lat = _mlp(P, f"encoders.{a}", n_enc, h, q)
         mu, lv = lat[:, :L], lat[:, L:]                           # model.py:149-150
         z = mu + eps[a].to(mu.dtype) * torch.exp(0.5 * lv)        # model.py:77-81
-        ai = actions[a].to(torch.int32).long().reshape(-1)        # model.py:146
-        embs.append(torch.nn.functional.embedding(ai, P[f"action_encoder.{a}.weight"]))
+        if spec.discrete_act:
+            ai = actions[a].to(torch.int32).long().reshape(-1)    # model.py:146
+            embs.append(torch.nn.functional.embedding(ai, P[f"action_encoder.{a}.weight"]))
+        else:                                                     # model.py:148: ActionEncoder MLP on the raw action vector
+            embs.append(_mlp(P, f"action_encoder.{a}", len(spec.act_hidden) + 1, _q(actions[a].to(mu.dtype), q), q))
         zs.append(z); mus.append(mu); lvs.append(lv)
     dec_in = _q(torch.cat(zs + embs, dim=-1), q)                   # model.py:158-164: all z, then all act-emb
     recon_s = _mlp(P, "state_decoder", n_dec, dec_in, q)

@@ -1,0 +1,84 @@
+"""Data-parallel train step on real GPUs (NCCL): run under torchrun with WORLD_SIZE ranks, one GPU each.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
+        tests/dp_gpu_check.py <fp32|bf16>
+
+Every rank holds the same parameters and takes rows [rank * Bl, (rank + 1) * Bl) of one global batch; after two
+train steps (bucketed all-reduce overlapped with backward, fused Adam) rank 0 compares losses, gradients and parameters
+with a single-process run of the FULL batch on its own GPU.  Philox eps is keyed by the global sample index, so both runs
+see identical noise.  One line: DP_CHECK {json}."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.dont_write_bytecode = True
+from oracle import mavae_oracle as O      # noqa: E402
+import mfvae_b200 as M                    # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+def main(precision):
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    dist.init_process_group("nccl", device_id=torch.device(dev))
+    spec = O.simple_tag_spec(latent=32)
+    Bl = 256
+    Bg = Bl * world
+    P = O.init_params(spec, 3)
+    g = torch.Generator().manual_seed(5)
+    S, A = spec.state_dim, spec.n_agents
+    obs, nxt = torch.randn(Bg, S, generator=g), torch.randn(Bg, S, generator=g)
+    act, rew = torch.randint(0, 5, (Bg, A), generator=g).float(), torch.randn(Bg, A, generator=g) * 3
+
+    def make():
+        m = M.MAVAE(spec.idx_features, spec.latent, spec.act_features, True, spec.agents, spec.obs_dim, spec.n_act, dev,
+                    precision=precision, include_dead_decoder=False)
+        m.load_named(P)
+        return m
+
+    def batch(lo, hi, sample0):
+        return M.PackedBatch(obs[lo:hi].to(dev), act[lo:hi].to(dev), nxt[lo:hi].to(dev), rew[lo:hi].to(dev),
+                             sample0=sample0, batch_global=Bg)
+
+    m = make()
+    m.enable_data_parallel()
+    losses = []
+    for step in range(2):
+        losses.append(m.train_step(batch(rank * Bl, (rank + 1) * Bl, rank * Bl), 1e-3).clone())
+    torch.cuda.synchronize()
+    out = {"precision": precision, "world": world, "batch_global": Bg}
+    if rank == 0:
+        ref = make()                       # single process, full batch
+        rl = []
+        for step in range(2):
+            rl.append(ref.train_step(batch(0, Bg, 0), 1e-3).clone())
+        torch.cuda.synchronize()
+        out["loss_rel"] = max(abs(float(a) - float(b)) / max(abs(float(b)), 1e-30) for x, y in zip(losses, rl) for a, b in zip(x, y))
+        mine, theirs = m.named_arena_tensors(), ref.named_arena_tensors()
+        reg = [k for k in mine if k.startswith(("state_decoder", "reward_decoder", "reward_linear", "idx_emb"))]
+        gr = {k: rel(mine[k].grad, theirs[k].grad) for k in reg}        # all-reduced (optimised) tensors
+        out["grad_rel_max"] = max(gr.values()); out["grad_rel_worst"] = max(gr, key=gr.get)
+        out["param_rel_max"] = max(rel(mine[k], theirs[k]) for k in reg)
+        print("DP_CHECK " + json.dumps(out), flush=True)
+    # every rank must hold identical parameters after the step
+    flat = m._arena[:m._n_opt].clone()
+    ref0 = flat.clone()
+    dist.broadcast(ref0, 0)
+    same = torch.tensor([float(torch.equal(flat, ref0))], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DP_SYNC " + json.dumps({"identical_params_on_all_ranks": bool(same.item() == 1.0)}), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else "fp32")

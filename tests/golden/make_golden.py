@@ -54,7 +54,8 @@ def ref_named_tensors(m):
         for n, p in enc.named_parameters():
             out[f"encoders.{a}.{n}"] = p
     for a, emb in m.action_encoder.items():
-        out[f"action_encoder.{a}.weight"] = emb.weight
+        for n, p in emb.named_parameters():            # Embedding: "weight"; ActionEncoder: "net.0.weight", ...
+            out[f"action_encoder.{a}.{n}"] = p
     return out
 
 
@@ -64,13 +65,16 @@ CASES = {
     "tiny_mse": (O.tiny_spec(3, idx_features=16, latent=8, act_features=8, include_dead_decoder=True), 16, 3, 4, 1.0, False),
     "latent32": (O.tiny_spec(4, idx_features=64, latent=32, act_features=64, include_dead_decoder=True), 64, 5, 6, 10.0, True),
     "default": (O.simple_tag_spec(include_dead_decoder=True), 128, 0, 0, 1.0, True),
+    # continuous actions: the ActionEncoder MLP replaces the action embedding (model.py:60-74,123,148)
+    "continuous": (O.tiny_spec(4, idx_features=64, latent=32, act_features=64, include_dead_decoder=True, discrete_act=False,
+                               act_dim={"adversary_0": 5, "adversary_1": 5, "adversary_2": 5, "agent_0": 3}), 64, 7, 8, 1.0, True),
 }
 
 
 def run_case(name, spec, B, pseed, dseed, rscale, huber):
     torch.manual_seed(0)
-    m = ref_model.MAVAE(spec.idx_features, spec.latent, spec.act_features, True, spec.agents,
-                        spec.obs_dim, spec.n_act, "cpu")
+    m = ref_model.MAVAE(spec.idx_features, spec.latent, spec.act_features, spec.discrete_act, spec.agents,
+                        spec.obs_dim, spec.n_act if spec.discrete_act else spec.act_dim, "cpu")
     P = O.init_params(spec, pseed)
     tensors = ref_named_tensors(m)
     assert set(tensors) == set(P), (set(tensors) ^ set(P))
@@ -133,8 +137,13 @@ def run_case(name, spec, B, pseed, dseed, rscale, huber):
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
+    only = sys.argv[1:]
     for name, args in CASES.items():
+        if only and name not in only:
+            continue
         run_case(name, *args)
+    if only:
+        sys.exit(0)
     # scheduler probe: lr the reference would use at selected steps
     opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], 0.005)
     sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=50, eta_min=1e-4)

@@ -15,6 +15,8 @@ SPECS = {
     "tiny_mse": lambda: O.tiny_spec(3, idx_features=16, latent=8, act_features=8, include_dead_decoder=True),
     "latent32": lambda: O.tiny_spec(4, idx_features=64, latent=32, act_features=64, include_dead_decoder=True),
     "default": lambda: O.simple_tag_spec(include_dead_decoder=True),
+    "continuous": lambda: O.tiny_spec(4, idx_features=64, latent=32, act_features=64, include_dead_decoder=True, discrete_act=False,
+                                      act_dim={"adversary_0": 5, "adversary_1": 5, "adversary_2": 5, "agent_0": 3}),
 }
 
 

@@ -31,7 +31,8 @@ def main(case, precision, engine, mode="dropin", rng="eps", fusion="auto"):
     spec, rec = load_case(case)
     dev = "cuda:0"
     huber = bool(rec["huber"])
-    m = M.MAVAE(spec.idx_features, spec.latent, spec.act_features, True, spec.agents, spec.obs_dim, spec.n_act, dev,
+    m = M.MAVAE(spec.idx_features, spec.latent, spec.act_features, spec.discrete_act, spec.agents, spec.obs_dim,
+                spec.n_act if spec.discrete_act else spec.act_dim, dev,
                 precision=precision, engine=engine, huber=huber, fusion=fusion)
     P = O.init_params(spec, int(rec["param_seed"]))
     m.load_named(P)

@@ -1,0 +1,36 @@
+"""-m gpu, needs >= 2 GPUs (skipped on a 1-GPU box): the NCCL data-parallel train step against the single-GPU step on
+the full batch (tests/dp_gpu_check.py under torchrun)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_dp2_matches_single_gpu(precision):
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(ROOT, "tests", "dp_gpu_check.py"), precision],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    lines = {l.split(" ", 1)[0]: json.loads(l.split(" ", 1)[1]) for l in r.stdout.splitlines() if l.startswith(("DP_CHECK ", "DP_SYNC "))}
+    assert r.returncode == 0 and "DP_CHECK" in lines and "DP_SYNC" in lines, r.stdout[-3000:] + r.stderr[-3000:]
+    o = lines["DP_CHECK"]
+    print(json.dumps(o))
+    assert lines["DP_SYNC"]["identical_params_on_all_ranks"]
+    if precision == "fp32":
+        assert o["loss_rel"] < 1e-5 and o["grad_rel_max"] < 1e-5 and o["param_rel_max"] < 1e-5, o
+    else:   # bf16: the two runs tile the batch dimension differently (split-K / accumulation order)
+        assert o["loss_rel"] < 1e-3 and o["grad_rel_max"] < 2e-2, o

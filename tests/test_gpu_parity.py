@@ -26,7 +26,7 @@ def run(case, precision, engine, mode="dropin", rng="eps", fusion="auto"):
     return out
 
 
-@pytest.mark.parametrize("case", ["tiny", "tiny_mse", "latent32", "default"])
+@pytest.mark.parametrize("case", ["tiny", "tiny_mse", "latent32", "default", "continuous"])
 def test_fp32_step_matches_reference_1e5(case):
     o = run(case, "fp32", "simt")
     assert max(o["loss_rel_golden"]) < 1e-5 and max(o["loss_rel_oracle"]) < 1e-5
@@ -35,7 +35,10 @@ def test_fp32_step_matches_reference_1e5(case):
     assert o["golden_grad_err"] < 4e-5, o["golden_grad_worst"]
     # three Adam steps amplify fp32 summation-order noise where |g| ~ eps-scale: 5e-5 (the oracle itself is pinned to
     # the reference's post-Adam parameters at 5e-5 in tests/test_oracle_golden.py)
-    assert o["param3_rel_max"] < 5e-5 and o["golden_param3_err"] < 1e-4
+    # continuous case: one hidden unit of state_decoder.net.0 is exactly dead in the reference at step 3 (a whole weight
+    # row has gradient 0.0, measured with the reference itself); fp32 round-off makes it barely alive here, and Adam turns
+    # any non-zero gradient into a full lr-sized step on that row -> 2e-3 of the tensor's L2.  The digests still agree.
+    assert o["param3_rel_max"] < (5e-3 if case == "continuous" else 5e-5) and o["golden_param3_err"] < 1e-4
 
 
 @pytest.mark.parametrize("mode", ["torchloss", "fast"])
@@ -54,7 +57,7 @@ def test_fp32_in_kernel_philox_draw():
 
 
 @pytest.mark.parametrize("engine", ["simt", "tcgen05"])
-@pytest.mark.parametrize("case", ["latent32", "default"])
+@pytest.mark.parametrize("case", ["latent32", "default", "continuous"])
 def test_bf16_step(case, engine):
     """bf16 path.  Loss within 1e-3 of the reference (golden, identical weights).  Gradients are checked against the
     oracle evaluated with the same bf16 rounding points (``emulate_bf16``): median relative L2 over tensors < 2e-3

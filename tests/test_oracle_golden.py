@@ -10,7 +10,7 @@ from tests.golden_util import load_case, digest, digest_close, step_inputs
 RTOL = 2e-5
 
 
-@pytest.mark.parametrize("name", ["tiny", "tiny_mse", "latent32", "default"])
+@pytest.mark.parametrize("name", ["tiny", "tiny_mse", "latent32", "default", "continuous"])
 def test_oracle_matches_reference_golden(name):
     spec, rec = load_case(name)
     L = spec.latent

@@ -1,0 +1,119 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: reparameterisation + KL / reconstruction-loss / Adam microbenchmarks, batch sweep 1K..1M,
+reported against the measured HBM roofline (MEASURED_PEAKS.json: STREAM-style copy).
+
+    python tools/microbench.py [--out gpurun_out/microbench.jsonl] [--max-batch 1048576]
+
+Kernels are called through the C ABI (mfvae_reparam_kl, mfvae_recon_loss, mfvae_adam_flat); timing = CUDA events on the
+launching stream around `iters` back-to-back launches over rotating buffer sets whose total size exceeds the 126 MB L2.
+Algorithmic bytes per sample: reparam+KL 3*A*L*4 (fp32 z), recon loss fwd+bwd 3*(S+A)*4 (fp32 gradient),
+Adam 28 B / parameter (+2 B bf16 shadow)."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+from mfvae_b200 import _lib as L    # noqa: E402
+
+A, LAT, S = 40, 64, 5660
+L2_BYTES = 126e6
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+def timed(fn, nsets, iters):
+    for i in range(3):
+        fn(i % nsets)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i % nsets)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "microbench.jsonl"))
+    ap.add_argument("--max-batch", type=int, default=1 << 20)
+    args = ap.parse_args()
+    lib = L.lib()
+    dev = "cuda:0"
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    pk, src = peak()
+    lines = []
+
+    def emit(kernel, B, bytes_per_launch, sec, extra=None):
+        gbs = bytes_per_launch / sec / 1e9
+        d = {"kernel": kernel, "batch": B, "us": round(sec * 1e6, 2), "algorithmic_bytes": bytes_per_launch,
+             "achieved_gbs": round(gbs, 1), "peak_gbs": pk, "peak_source": src, "frac": round(gbs / pk, 4)}
+        d.update(extra or {})
+        lines.append(d)
+        print(json.dumps(d), flush=True)
+
+    B = 1024
+    while B <= args.max_batch:
+        W = A * LAT
+        # ---- reparameterisation + KL (fp32 z: 3 * W * 4 bytes per sample) ----
+        per = 3 * W * 4 * B
+        nsets = max(1, min(8, int(2 * L2_BYTES // per) + 1))
+        mus = [torch.randn(B, W, device=dev) * 0.5 for _ in range(nsets)]
+        lvs = [torch.randn(B, W, device=dev) * 0.3 for _ in range(nsets)]
+        zs = [torch.empty(B, W, device=dev) for _ in range(nsets)]
+        kl = torch.zeros(4, device=dev); scratch = torch.zeros(4096, device=dev)
+        iters = max(5, min(200, int(2e9 // per)))
+        sec = timed(lambda k: L.check(lib.mfvae_reparam_kl(L.ptr(mus[k]), L.ptr(lvs[k]), None, L.ptr(zs[k]), 0, B, W, 0x5EED, 0, 0, B,
+                                                           L.ptr(kl), L.ptr(scratch), st)), nsets, iters)
+        emit("reparam_kl_fwd (fp32 z, Philox eps in registers)", B, per, sec, {"bytes_per_sample": 3 * W * 4})
+        zb = [torch.empty(B, W, device=dev, dtype=torch.bfloat16) for _ in range(nsets)]
+        perb = (2 * 4 + 2) * W * B
+        sec = timed(lambda k: L.check(lib.mfvae_reparam_kl(L.ptr(mus[k]), L.ptr(lvs[k]), None, L.ptr(zb[k]), 1, B, W, 0x5EED, 0, 0, B,
+                                                           L.ptr(kl), L.ptr(scratch), st)), nsets, iters)
+        emit("reparam_kl_fwd (bf16 z, the train-step variant)", B, perb, sec, {"bytes_per_sample": (2 * 4 + 2) * W})
+        del mus, lvs, zs, zb
+        # ---- reconstruction loss forward value + gradient (fp32 gradient: 3 * (S + A) * 4 bytes per sample) ----
+        Wd = S + A
+        per = 3 * Wd * 4 * B
+        nsets = max(1, min(8, int(2 * L2_BYTES // per) + 1))
+        rec = [torch.randn(B, Wd, device=dev) for _ in range(nsets)]
+        tgt = [torch.randn(B, Wd, device=dev) * 2 for _ in range(nsets)]
+        gr = [torch.empty(B, Wd, device=dev) for _ in range(nsets)]
+        iters = max(5, min(200, int(2e9 // per)))
+        sec = timed(lambda k: L.check(lib.mfvae_recon_loss(L.ptr(rec[k]), Wd, L.ptr(tgt[k]), Wd, L.ptr(gr[k]), Wd, 0, B, Wd, 1, 1.0, B * Wd,
+                                                           L.ptr(kl), L.ptr(scratch), st)), nsets, iters)
+        emit("recon_loss fwd+bwd (Huber, fp32 gradient)", B, per, sec, {"bytes_per_sample": 3 * Wd * 4})
+        del rec, tgt, gr
+        torch.cuda.empty_cache()
+        B *= 4
+    # ---- Adam over the registered parameters of the reference model (17,451,820 -> padded arena prefix) ----
+    n = 17_451_824
+    p = torch.randn(n, device=dev); g = torch.randn(n, device=dev) * 1e-3
+    m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev); sh = torch.empty(n, device=dev, dtype=torch.bfloat16)
+    t = [0]
+
+    def adam(_):
+        t[0] += 1
+        L.check(lib.mfvae_adam_flat(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), L.ptr(sh), n, 1e-3, 0.9, 0.999, 1e-8, t[0], st))
+    sec = timed(adam, 1, 50)
+    emit("adam (fp32 p/g/m/v + bf16 shadow)", n, 30 * n, sec, {"bytes_per_param": 30, "note": "489 MB working set > L2"})
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as f:
+        for d in lines:
+            f.write(json.dumps(d) + "\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -349,8 +349,15 @@ def run_ours(args, w):
         if tot_ms > 0:
             ach = tot_fl / (tot_ms * 1e-3) / 1e12
             bound = "tensor" if w["precision"] == "bf16" else "fp32-simt"
+            # DRAM traffic of the same launches: dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu launch list
+            # (profiles/r1_traffic.json); only valid for the workload / batch it was captured on
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+            if args.workload == "cfg2" and B == 4096 and os.path.exists(tp):
+                traffic = json.load(open(tp))["cfg2_b4096"]["gemm_tc_kernel_all_launches"]["dram_bytes_per_step"]
             roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                    "traffic": None, "kernel": "gemm_tc_kernel (all %d GEMM launches of one step)" % len(rows),
+                    "traffic": traffic, "traffic_note": "bytes per step over the same 36 launches (ncu, profiles/r1_traffic.json)",
+                    "kernel": "gemm_tc_kernel (all %d GEMM launches of one step)" % len(rows),
                     "gemm_ms_per_step": tot_ms, "gemm_flop_per_step": tot_fl, "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
                     "engine": bound, "top": rows[:8], "all": rows}
 

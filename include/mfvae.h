@@ -157,6 +157,12 @@ int mfvae_adam_step(MfvaeHandle h, float lr, float beta1, float beta2, float eps
 /* same update; the decoder block runs on an internal stream as soon as its gradient buckets are final (overlapping the
  * encoder half of backward).  Only valid when no collective has to run between backward and the update (1 GPU). */
 int mfvae_adam_step_overlapped(MfvaeHandle h, float lr, float beta1, float beta2, float eps, int64_t t, void* stream);
+/* data parallel: Adam over one arena range (a gradient bucket, 8-element aligned, inside the optimised prefix) on `stream`
+ * -- issued on the communication stream right behind that bucket's all-reduce -- and the guard that makes `stream` wait
+ * until the backward pass in flight no longer reads the decoder weights (needed before updating buckets 0..2). */
+int mfvae_adam_range(MfvaeHandle h, int64_t begin, int64_t end, float lr, float beta1, float beta2, float eps, int64_t t,
+                     void* stream);
+int mfvae_wait_decoder_reads(MfvaeHandle h, void* stream);
 /* forward + loss + backward in one call (no optimizer; the host all-reduces gradients in between).  With
  * MFVAE_FUSE_LOSS out->d_recon_s is NULL (see above). */
 int mfvae_fwd_bwd(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* stream);

@@ -77,6 +77,8 @@ SIGNATURES = {
     "mfvae_backward_ext": (C.c_int, [_vp, C.POINTER(MfvaeBatch), _vp, _i64, _vp, _i64, _vp, _vp]),
     "mfvae_adam_step": (C.c_int, [_vp, _f, _f, _f, _f, _i64, _vp]),
     "mfvae_adam_step_overlapped": (C.c_int, [_vp, _f, _f, _f, _f, _i64, _vp]),
+    "mfvae_adam_range": (C.c_int, [_vp, _i64, _i64, _f, _f, _f, _f, _i64, _vp]),
+    "mfvae_wait_decoder_reads": (C.c_int, [_vp, _vp]),
     "mfvae_fwd_bwd": (C.c_int, [_vp, C.POINTER(MfvaeBatch), C.POINTER(MfvaeOutputs), _vp]),
     "mfvae_launch_count": (C.c_uint64, []),
     "mfvae_profile_enable": (C.c_int, [_vp, _i32]),

@@ -911,6 +911,23 @@ int mfvae_adam_step_overlapped(MfvaeHandle h, float lr, float beta1, float beta2
   return 0;
 }
 
+// Adam over one arena range (a gradient bucket) on `stream`: data parallel runs it per bucket on the communication stream
+// right behind that bucket's all-reduce, so the optimizer sweep overlaps the rest of backward.
+int mfvae_adam_range(MfvaeHandle h, int64_t begin, int64_t end, float lr, float beta1, float beta2, float eps, int64_t t, void* stream) {
+  MFVAE_CHECK(h && h->ar.d_param, "arenas are not bound");
+  MFVAE_CHECK(begin >= 0 && end <= h->optimized_elems && begin % 8 == 0, "adam range must lie inside the optimised prefix, 8-element aligned");
+  if (end <= begin) return 0;
+  __nv_bfloat16* sh = static_cast<__nv_bfloat16*>(h->ar.d_shadow_bf16);
+  return launch_adam(h->ar.d_param + begin, h->ar.d_grad + begin, h->ar.d_m + begin, h->ar.d_v + begin, sh ? sh + begin : nullptr,
+                     end - begin, lr, beta1, beta2, eps, t, static_cast<cudaStream_t>(stream));
+}
+// make `stream` wait until the backward pass in flight has finished READING the decoder / output-layer weights
+int mfvae_wait_decoder_reads(MfvaeHandle h, void* stream) {
+  MFVAE_CHECK(h && h->dec_read_ev, "no backward pass has been recorded");
+  MFVAE_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->dec_read_ev, 0));
+  return 0;
+}
+
 uint64_t mfvae_launch_count(void) { return g_launch_count; }
 
 int mfvae_profile_enable(MfvaeHandle h, int32_t on) {

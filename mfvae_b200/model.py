@@ -566,10 +566,12 @@ class MAVAE(nn.Module):
                 out.append((i, b.value, e.value))
         return out
 
-    def _allreduce_grads(self):
+    def _allreduce_grads(self, adam=None):
         """SUM all-reduce of the gradient buckets (the loss-gradient kernels already divide by the GLOBAL batch, so
         no averaging pass is needed) and of the 4 partial loss scalars.  On the GPU each bucket is reduced on the
-        side stream as soon as its completion event fires, overlapping the rest of backward."""
+        communication stream as soon as its completion event fires, overlapping the rest of backward; with
+        ``adam=(lr, betas, eps)`` the fused Adam of that bucket follows on the same stream right behind its all-reduce,
+        so the optimizer sweep is hidden behind the encoder half of backward as well."""
         import torch.distributed as dist
         buckets = self.grad_buckets()
         if not self._on_gpu:           # host-logic path exercised by the gloo tests; no compute happens on CPU
@@ -579,17 +581,26 @@ class MAVAE(nn.Module):
                 dist.all_reduce(self._losses, group=self._pg)
             return
         lib = L.lib()
-        works = []
         main = torch.cuda.current_stream(self._tdev)
-        with torch.cuda.stream(self._comm_stream):
+        cs = self._comm_stream
+        csp = C.c_void_p(cs.cuda_stream)
+        if adam is not None:
+            self._adam_t += 1
+        guarded = False
+        with torch.cuda.stream(cs):
             for i, b, e in buckets:
-                L.check(lib.mfvae_bucket_wait(self._h, i, C.c_void_p(self._comm_stream.cuda_stream)))
-                works.append(dist.all_reduce(self._grad[b:e], group=self._pg, async_op=True))
-            self._comm_stream.wait_stream(main)       # losses are final at the end of the main stream's queue
-            works.append(dist.all_reduce(self._losses, group=self._pg, async_op=True))
-        for w in works:
-            w.wait()
-        main.wait_stream(self._comm_stream)
+                L.check(lib.mfvae_bucket_wait(self._h, i, csp))
+                dist.all_reduce(self._grad[b:e], group=self._pg, async_op=True).wait()     # cs waits for NCCL
+                if adam is not None:
+                    if not guarded:     # backward may still be reading the decoder weights these buckets hold
+                        L.check(lib.mfvae_wait_decoder_reads(self._h, csp))
+                        guarded = True
+                    lr, betas, eps = adam
+                    L.check(lib.mfvae_adam_range(self._h, b, min(e, self._n_opt), float(lr), float(betas[0]), float(betas[1]),
+                                                 float(eps), self._adam_t, csp))
+            cs.wait_stream(main)       # losses are final at the end of the main stream's queue
+            dist.all_reduce(self._losses, group=self._pg, async_op=True).wait()
+        main.wait_stream(cs)
 
     def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, overlapped=False):
         """Fused Adam over the registered (optimised) prefix of the arena; also refreshes the bf16 shadow.
@@ -636,6 +647,7 @@ class MAVAE(nn.Module):
         self._losses = self._ws_view(out.d_losses, 1, 4, 4)[0]
         self.philox_step += 1
         if self.data_parallel:
-            self._allreduce_grads()
-        self.adam_step(lr, betas, eps, overlapped=not self.data_parallel)
+            self._allreduce_grads(adam=(lr, betas, eps))      # per-bucket all-reduce + Adam on the communication stream
+        else:
+            self.adam_step(lr, betas, eps, overlapped=True)
         return self._losses

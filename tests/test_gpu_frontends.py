@@ -1,0 +1,93 @@
+"""-m gpu: the callers either side of the hot path: evaluation step, the jax_ver ELBO weighting and its
+train_step / test_step pair, and the replay ring feeding train steps."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(precision="fp32", **kw):
+    import mfvae_b200 as M
+    from oracle import mavae_oracle as O
+    spec = O.tiny_spec(4, idx_features=64, latent=32, act_features=64)
+    m = M.MAVAE(spec.idx_features, spec.latent, spec.act_features, True, spec.agents, spec.obs_dim, spec.n_act, "cuda:0",
+                precision=precision, include_dead_decoder=False, **kw)
+    m.load_named(O.init_params(spec, 11))
+    return M, O, spec, m
+
+
+def _batch(M, spec, B, seed=3):
+    g = torch.Generator(device="cuda:0").manual_seed(seed)
+    S, A = spec.state_dim, spec.n_agents
+    return M.PackedBatch(torch.randn(B, S, device="cuda:0", generator=g),
+                         torch.randint(0, 5, (B, A), device="cuda:0", generator=g).float(),
+                         torch.randn(B, S, device="cuda:0", generator=g), torch.randn(B, A, device="cuda:0", generator=g) * 4)
+
+
+def test_test_step_equals_train_step_losses_and_leaves_state_alone():
+    M, O, spec, m = _model()
+    pb = _batch(M, spec, 96)
+    before = m._arena.clone()
+    ev = m.test_step(pb).clone()
+    assert torch.equal(m._arena, before) and m.philox_step == 0           # no update, Philox step not advanced
+    tr = m.train_step(pb, 0.0).clone()                                    # same Philox step -> same eps
+    assert torch.allclose(ev, tr, rtol=1e-6, atol=0)
+    # against the oracle on the kernel's own eps stream
+    eps_all = torch.from_numpy(O.philox_normal(m.philox_seed, 0, 0, 96, spec.n_agents * spec.latent).astype(np.float32))
+    L = spec.latent
+    idx_state = {a: torch.cat([torch.full((96, 1), float(i)), pb.obs[:, sum(spec.obs_dim[x] for x in spec.agents[:i]):][:, :spec.obs_dim[a]].cpu()], 1)
+                 for i, a in enumerate(spec.agents)}
+    acts = {a: pb.act[:, i:i + 1].cpu() for i, a in enumerate(spec.agents)}
+    eps = {a: eps_all[:, i * L:(i + 1) * L] for i, a in enumerate(spec.agents)}
+    want, _, _ = O.grads(O.init_params(spec, 11), spec, idx_state, acts, eps, pb.next.cpu(), pb.rew.cpu())
+    for g, w in zip(ev.cpu().tolist(), want):
+        assert abs(g - w) <= 1e-5 * abs(w)
+
+
+def test_jax_weighting_is_the_weighted_sum_of_the_three_terms():
+    """jax_ver/trainer.py:42-43,64: loss = 0.5 s + 0.5 r + 0.1 kl.  Gradients are linear in the three weights, so the jax
+    step's gradients must equal the same combination of the single-term gradients (fp32 engine, 1e-5)."""
+    M, O, spec, m = _model()
+    from mfvae_b200 import jax_trainer as J
+    pb = _batch(M, spec, 64)
+
+    def grads(weights):
+        m.philox_step = 0
+        losses = m.train_step(pb, 0.0, loss_weights=weights).clone()
+        return losses, m._grad.clone()
+
+    l_s, g_s = grads((0.0, 0.0, 1.0))
+    l_r, g_r = grads((0.0, 1.0, 0.0))
+    l_k, g_k = grads((1.0, 0.0, 0.0))
+    m.philox_step = 0
+    l_j = J.train_step(m, pb, lr=0.0).clone()
+    g_j = m._grad.clone()
+    kw, rw, sw = J.loss_weights()
+    assert (kw, rw, sw) == (0.1, 0.5, 0.5)
+    want = sw * g_s + rw * g_r + kw * g_k
+    assert float((g_j - want).norm() / want.norm()) < 1e-5
+    assert abs(float(l_j[0]) - (sw * float(l_j[1]) + rw * float(l_j[2]) + kw * float(l_j[3]))) < 1e-6
+    assert torch.allclose(l_j[1:], l_s[1:], rtol=1e-6)                   # the three raw terms do not depend on the weights
+    m.philox_step = 0
+    assert torch.allclose(J.test_step(m, pb), l_j, rtol=1e-6)
+
+
+def test_ring_fed_train_steps_match_host_fed():
+    """The replay ring (reference MultiAgentCPPRB / JaxFbxBuffer replacement) hands the step the same rows the host
+    path would: sample indices -> gather on the device == indexing the host copy of the stored rows."""
+    M, O, spec, m = _model()
+    ring = M.DeviceRing(spec.agents, spec.obs_dim, capacity=300, device="cuda:0")
+    g = torch.Generator().manual_seed(9)
+    rows = torch.randn(300, ring.row, generator=g)
+    S, A = ring.S, ring.A
+    rows[:, S:S + A] = torch.randint(0, 5, (300, A), generator=g).float()
+    ring.add_rows_device(rows.cuda())
+    pb, idx = ring.sample_packed(128, seed=5, with_indices=True)
+    take = rows[idx.cpu().long()]
+    assert torch.equal(pb.obs.cpu(), take[:, :S]) and torch.equal(pb.act.cpu(), take[:, S:S + A])
+    assert torch.equal(pb.next.cpu(), take[:, S + A:2 * S + A]) and torch.equal(pb.rew.cpu(), take[:, 2 * S + A:2 * S + 2 * A])
+    a = m.test_step(pb).clone()
+    host = M.PackedBatch(take[:, :S].cuda(), take[:, S:S + A].cuda(), take[:, S + A:2 * S + A].cuda(), take[:, 2 * S + A:2 * S + 2 * A].cuda())
+    b = m.test_step(host).clone()
+    assert torch.equal(a, b)

@@ -29,7 +29,9 @@ static inline int grid_for(int64_t work_items, int per_sm = 8) {
 // stage: packed fp32 rows -> encoder input X0[a][b][:] = [idx_emb[id] | obs_a | 0] and the action-embedding
 // half of the decoder input.
 // ---------------------------------------------------------------------------------------------
-// grid = (row chunks, A); block = 256 threads = (256 / VL) rows x VL column strips of 4
+// grid = (row chunks, A); block = 256 threads = (256 / VL) rows x VL column strips of 4.  A thread keeps its strip and
+// walks the rows four at a time: the strip's role (embedding / interior of the observation / edge) and the load width its
+// alignment allows are fixed per thread, so the four rows' loads are straight-line and in flight together.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) stage_kernel(StageArgs p) {
   const int a = blockIdx.y;
@@ -39,37 +41,47 @@ __global__ void __launch_bounds__(kThreads) stage_kernel(StageArgs p) {
   const int strip0 = threadIdx.x % VL, rphase = threadIdx.x / VL;
   const int od = p.obs_dim[a], off = p.obs_off[a];
   T* x0 = static_cast<T*>(p.x0) + a * p.x0_gs;
-  for (int b = blockIdx.x * rows_per_pass + rphase; b < p.B; b += gridDim.x * rows_per_pass) {
-    int id = a;
-    if (p.idx) id = static_cast<int>(p.idx[static_cast<int64_t>(b) * p.A + a]);
-    const float* orow = p.obs + static_cast<int64_t>(b) * p.obs_ld + off;
-    for (int strip = strip0; strip < nvec; strip += VL) {
-      const int c0 = strip * 4;
-      float v[4];
-      if (c0 >= p.I && c0 + 3 < p.I + od) {
-        // interior strip of the observation: widest aligned load the agent's column offset allows
-        const float* src = orow + (c0 - p.I);
-        const uintptr_t ad = reinterpret_cast<uintptr_t>(src);
-        if ((ad & 15) == 0) {
-          const float4 t = ldg_stream4(src);
-          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        } else if ((ad & 7) == 0) {
-          const float2 t0 = __ldg(reinterpret_cast<const float2*>(src)), t1 = __ldg(reinterpret_cast<const float2*>(src) + 1);
-          v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
-        } else {
-          v[0] = __ldg(src); v[1] = __ldg(src + 1); v[2] = __ldg(src + 2); v[3] = __ldg(src + 3);
-        }
-      } else {
+  const int rstep = gridDim.x * rows_per_pass;
+  constexpr int U = 4;
+  for (int strip = strip0; strip < nvec; strip += VL) {
+    const int c0 = strip * 4;
+    const bool interior = c0 >= p.I && c0 + 3 < p.I + od;
+    const float* src0 = p.obs + off + (c0 - p.I);
+    // row pitch and base decide the widest aligned load for every row of this strip
+    const uintptr_t al = reinterpret_cast<uintptr_t>(src0) | (static_cast<uintptr_t>(p.obs_ld) << 2);
+    const int mode = !interior ? 0 : ((al & 15) == 0 ? 3 : ((al & 7) == 0 ? 2 : 1));
+    for (int b = blockIdx.x * rows_per_pass + rphase; b < p.B; b += U * rstep) {
+      float v[U][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = c0 + k;
-          float x = 0.f;
-          if (c < p.I) x = p.idx_emb[static_cast<int64_t>(id) * p.I + c];
-          else if (c < p.I + od) x = __ldg(orow + (c - p.I));
-          v[k] = x;
+      for (int u = 0; u < U; ++u) {
+        const int bb = min(b + u * rstep, p.B - 1);                 // clamped rows are loaded twice, stored once
+        const float* src = src0 + static_cast<int64_t>(bb) * p.obs_ld;
+        if (mode == 3) {
+          const float4 t = ldg_stream4(src);
+          v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w;
+        } else if (mode == 2) {
+          const float2 t0 = __ldg(reinterpret_cast<const float2*>(src)), t1 = __ldg(reinterpret_cast<const float2*>(src) + 1);
+          v[u][0] = t0.x; v[u][1] = t0.y; v[u][2] = t1.x; v[u][3] = t1.y;
+        } else if (mode == 1) {
+          v[u][0] = __ldg(src); v[u][1] = __ldg(src + 1); v[u][2] = __ldg(src + 2); v[u][3] = __ldg(src + 3);
+        } else {
+          int id = a;
+          if (p.idx) id = static_cast<int>(p.idx[static_cast<int64_t>(bb) * p.A + a]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = c0 + k;
+            float x = 0.f;
+            if (c < p.I) x = p.idx_emb[static_cast<int64_t>(id) * p.I + c];
+            else if (c < p.I + od) x = __ldg(src + k);
+            v[u][k] = x;
+          }
         }
       }
-      store4<T>(x0 + static_cast<int64_t>(b) * p.x0_ld + c0, make_float4(v[0], v[1], v[2], v[3]));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int bb = b + u * rstep;
+        if (bb < p.B) store4<T>(x0 + static_cast<int64_t>(bb) * p.x0_ld + c0, make_float4(v[u][0], v[u][1], v[u][2], v[u][3]));
+      }
     }
   }
 }

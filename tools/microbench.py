@@ -83,6 +83,15 @@ def main():
         sec = timed(lambda k: L.check(lib.mfvae_reparam_kl(L.ptr(mus[k]), L.ptr(lvs[k]), None, L.ptr(zb[k]), 1, B, W, 0x5EED, 0, 0, B,
                                                            L.ptr(kl), L.ptr(scratch), st)), nsets, iters)
         emit("reparam_kl_fwd (bf16 z, the train-step variant)", B, perb, sec, {"bytes_per_sample": (2 * 4 + 2) * W})
+        # explicit eps read from HBM instead of the in-register Philox + Box-Muller draw: isolates the memory path
+        # (the Philox variants above are bound by the integer / transcendental work of the generator, not by HBM)
+        if 4 * W * 4 * B * nsets < 60e9:
+            epss = [torch.randn(B, W, device=dev) for _ in range(nsets)]
+            pere = 4 * W * 4 * B
+            sec = timed(lambda k: L.check(lib.mfvae_reparam_kl(L.ptr(mus[k]), L.ptr(lvs[k]), L.ptr(epss[k]), L.ptr(zs[k]), 0, B, W, 0x5EED, 0, 0, B,
+                                                               L.ptr(kl), L.ptr(scratch), st)), nsets, iters)
+            emit("reparam_kl_fwd (fp32 z, eps read from HBM)", B, pere, sec, {"bytes_per_sample": 4 * W * 4})
+            del epss
         del mus, lvs, zs, zb
         # ---- reconstruction loss forward value + gradient (fp32 gradient: 3 * (S + A) * 4 bytes per sample) ----
         Wd = S + A

@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kThreads) recon_loss_kernel(ReconLossArgs p) {
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
       const int64_t b = i / wq;
       const int c = static_cast<int>(i - b * wq) * 4;
-      const float4 r = ldg_stream4(p.recon + b * p.recon_ld + c);
+      const float4 r = p.recon16 ? load4<__nv_bfloat16>(p.recon16 + b * p.grad_ld + c) : ldg_stream4(p.recon + b * p.recon_ld + c);
       const float4 t = ldg_stream4(p.target + b * p.target_ld + c);
       float4 g; float v0, v1, v2, v3;
       recon_elem(r.x, t.x, p.huber, p.grad_scale, v0, g.x);
@@ -310,7 +310,8 @@ __global__ void __launch_bounds__(kThreads) recon_loss_kernel(ReconLossArgs p) {
       const int64_t b = i / p.width;
       const int c = static_cast<int>(i - b * p.width);
       float v, g;
-      recon_elem(p.recon[b * p.recon_ld + c], p.target[b * p.target_ld + c], p.huber, p.grad_scale, v, g);
+      const float r = p.recon16 ? __bfloat162float(p.recon16[b * p.grad_ld + c]) : p.recon[b * p.recon_ld + c];
+      recon_elem(r, p.target[b * p.target_ld + c], p.huber, p.grad_scale, v, g);
       acc += v;
       if (grad) grad[b * p.grad_ld + c] = from_f<T>(g);
     }
@@ -320,8 +321,8 @@ __global__ void __launch_bounds__(kThreads) recon_loss_kernel(ReconLossArgs p) {
 }
 
 int launch_recon_loss(const ReconLossArgs& a, cudaStream_t s) {
-  const bool vec = a.width % 4 == 0 && a.recon_ld % 4 == 0 && a.target_ld % 4 == 0 && a.grad_ld % 4 == 0 &&
-                   (reinterpret_cast<uintptr_t>(a.recon) % 16 == 0) && (reinterpret_cast<uintptr_t>(a.target) % 16 == 0) &&
+  const bool vec = a.width % 4 == 0 && (a.recon16 || a.recon_ld % 4 == 0) && a.target_ld % 4 == 0 && a.grad_ld % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(a.recon16 ? static_cast<const void*>(a.recon16) : static_cast<const void*>(a.recon)) % 16 == 0) && (reinterpret_cast<uintptr_t>(a.target) % 16 == 0) &&
                    (reinterpret_cast<uintptr_t>(a.grad) % 16 == 0);
   const int64_t items = vec ? a.B * (a.width / 4) : a.B * a.width;
   const int grid = grid_for(items);

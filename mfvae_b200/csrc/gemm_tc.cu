@@ -483,6 +483,7 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
   pl->op = op;
   const int m_tiles = (op.M + BM - 1) / BM;
   // tile width: the widest BN that still gives every SM a tile; otherwise the narrowest that covers N
+  const int k_blocks = (op.K + BK - 1) / BK;
   int BN = 64;
   {
     const int cands[3] = {256, 128, 64};
@@ -491,8 +492,21 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
       const long long t = static_cast<long long>(op.G) * m_tiles * ((op.N + c - 1) / c);
       if (t >= kNumSMs) { BN = c; break; }
     }
+    // K-long GEMMs are bound by operand traffic from L2 (a 128 x BN x 64 step moves (128 + BN) * 128 bytes for
+    // 128 * BN * 128 flops): a narrower tile that fills more SMs loses more to bandwidth than the idle SMs cost.
+    // Model: time ~ waves * BN / eff(BN), eff measured on this kernel (tile GEMM rate relative to BN = 256).
+    if (k_blocks > 16 && op.epi != kEpiAccum) {
+      const double eff[3] = {1.0, 0.65, 0.35};
+      double best = 1e30;
+      for (int i = 0; i < 3; ++i) {
+        const int c = cands[i];
+        if (c > 64 && c / 2 >= op.N) continue;
+        const long long t = static_cast<long long>(op.G) * m_tiles * ((op.N + c - 1) / c);
+        const double cost = static_cast<double>((t + kNumSMs - 1) / kNumSMs) * c / eff[i];
+        if (cost < best) { best = cost; BN = c; }
+      }
+    }
   }
-  const int k_blocks = (op.K + BK - 1) / BK;
   // Narrow tiles, three co-resident CTAs per SM (75 KB smem, 128 TMEM columns each) when
   //  * K <= 256: the tile is a handful of MMAs plus an epilogue, latency hiding comes from the neighbours; or
   //  * 128-wide tiles cannot give every SM one tile anyway (the small layers): a CTA of this shape leaves room for the

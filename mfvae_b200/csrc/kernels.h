@@ -52,6 +52,7 @@ int launch_reparam_kl_bwd(const ReparamBwdArgs& a, cudaStream_t s);
 
 struct ReconLossArgs {
   const float* recon; int64_t recon_ld;
+  const __nv_bfloat16* recon16;                  // when set: the reconstruction in bf16 (same ld as grad; may alias grad: in-place)
   const float* target; int64_t target_ld;
   void* grad; int64_t grad_ld; int grad_dtype;   // may be nullptr (forward value only)
   int64_t B; int width;

@@ -73,7 +73,8 @@ struct MfvaeHandle_ {
   EncFusedPlan* enc_fused = nullptr;         // fused per-agent encoder chain (enc_fused.cu), when its shape constraints hold
   std::vector<int> g_enc_fwd, g_enc_wg, g_enc_dg, g_dec_fwd, g_dec_wg, g_dec_dg;
   int g_sout_fwd = -1, g_rout_fwd = -1, g_rl_fwd = -1;
-  int g_sout_loss = -1;                      // state output layer with the reconstruction loss + its gradient as the epilogue
+  int g_sout_loss = -1;
+  int g_sout_fwd16 = -1;                     // train step: recon_s written once, in bf16, into the D(recon_s) buffer (loss runs in place)                      // state output layer with the reconstruction loss + its gradient as the epilogue
   int g_act_fwd1 = -1, g_act_fwd2 = -1, g_act_wg2 = -1, g_act_dg2 = -1, g_act_wg1 = -1;
   int g_sout_wg = -1, g_sout_dg = -1, g_rout_wg = -1, g_rout_dg = -1, g_rl_wg = -1, g_rl_dg = -1;
 
@@ -377,6 +378,7 @@ static int build_ops(MfvaeHandle_* h) {
     if (h->use_tc) {
       h->g_sout_loss = fwd(1, B, h->S, HL, hs, 0, hld, wptr(h->sOutW.off), 0, HL, buf(h->DRS), 0, h->DRS.ld, dt, P + h->sOutB.off, 0, false);
       h->gemms[h->g_sout_loss].epi = kEpiLossGrad;
+      h->g_sout_fwd16 = fwd(1, B, h->S, HL, hs, 0, hld, wptr(h->sOutW.off), 0, HL, buf(h->DRS), 0, h->DRS.ld, dt, P + h->sOutB.off, 0, false);
     }
     h->g_rout_fwd = fwd(1, B, A, HL, hr, 0, hld, wptr(h->rOutW.off), 0, HL, buf(h->RR0), 0, h->RR0.ld, dt, P + h->rOutB.off, 0, false);
     h->g_rl_fwd = fwd(1, B, A, A, buf(h->RR0), 0, h->RR0.ld, wptr(h->rlW.off), 0, h->Ap, buf(h->RR), 0, h->RR.ld, kF32, P + h->rlb.off, 0, false);
@@ -454,7 +456,7 @@ static int do_forward_act_embed(MfvaeHandle_* h, const StageArgs& st, cudaStream
 
 // loss_batch != nullptr (train step): the state output layer runs with the loss epilogue -- recon_s is not materialised,
 // D(recon_s) and the per-warp loss partials come straight out of the GEMM (the target must be bound in the batch).
-static int do_forward_decoders(MfvaeHandle_* h, cudaStream_t s, const MfvaeBatch* loss_batch = nullptr, int huber = 1) {
+static int do_forward_decoders(MfvaeHandle_* h, cudaStream_t s, const MfvaeBatch* loss_batch = nullptr, int huber = 1, bool recon16 = false) {
   const bool aux = use_aux(h);
   if (aux) MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join_ev, 0));     // action embeddings are in ZIN
   for (int l = 0; l < h->cfg.n_dec_hidden; ++l) MFVAE_TRY(run_gemm(h, h->g_dec_fwd[l], s));
@@ -470,6 +472,8 @@ static int do_forward_decoders(MfvaeHandle_* h, cudaStream_t s, const MfvaeBatch
     MFVAE_TRY(gemm_tc_set_loss(h->tc[h->g_sout_loss], loss_batch->d_next, h->S, static_cast<float>(static_cast<double>(h->s_weight) / cs), huber,
                                scratch_ptr(h, 1)));
     MFVAE_TRY(run_gemm(h, h->g_sout_loss, s));
+  } else if (recon16) {
+    MFVAE_TRY(run_gemm(h, h->g_sout_fwd16, s));
   } else {
     MFVAE_TRY(run_gemm(h, h->g_sout_fwd, s));
   }
@@ -482,7 +486,7 @@ static int do_forward_decoders(MfvaeHandle_* h, cudaStream_t s, const MfvaeBatch
   return 0;
 }
 
-static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, cudaStream_t s, bool fuse_loss = false) {
+static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, cudaStream_t s, bool fuse_loss = false, bool recon16 = false) {
   MFVAE_TRY(check_ready(h, b));
   const MfvaeBatch* lb = fuse_loss ? b : nullptr;
   StageArgs st{};
@@ -498,7 +502,7 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
     out->d_recon_s = reinterpret_cast<const float*>(h->ws + h->RS.off); out->recon_s_ld = static_cast<int32_t>(h->RS.ld);
     out->d_recon_r = reinterpret_cast<const float*>(h->ws + h->RR.off); out->recon_r_ld = static_cast<int32_t>(h->RR.ld);
     out->d_latent = lat; out->d_losses = losses_ptr(h);
-    if (fuse_loss) { out->d_recon_s = nullptr; out->recon_s_ld = 0; }      // never written on this path
+    if (fuse_loss || recon16) { out->d_recon_s = nullptr; out->recon_s_ld = 0; }      // not materialised in fp32 on this path
   }
   if (h->enc_fused) {
     // staging of X0, the four encoder layers, reparameterisation and KL: one kernel (enc_fused.cu)
@@ -508,7 +512,7 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
     eb.eps = b->d_eps; eb.eps_ld = static_cast<int64_t>(h->A) * h->L; eb.seed = b->seed; eb.step = b->step; eb.sample0 = b->sample0;
     eb.kl_scale = 1.0f / static_cast<float>(b->batch_global); eb.kl_out = losses_ptr(h) + 3; eb.scratch = scratch_ptr(h, 0);
     MFVAE_TRY(enc_fused_forward(h->enc_fused, eb, s));
-    return do_forward_decoders(h, s, lb, h->cfg.huber);
+    return do_forward_decoders(h, s, lb, h->cfg.huber, recon16);
   }
   MFVAE_TRY(do_forward_act_embed(h, st, s));
   MFVAE_TRY(launch_stage(st, s, true, false));
@@ -521,10 +525,10 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
   rp.kl_scale = 1.0f / static_cast<float>(b->batch_global);
   rp.kl_out = losses_ptr(h) + 3; rp.scratch = scratch_ptr(h, 0);
   MFVAE_TRY(launch_reparam_kl_fwd(rp, s));
-  return do_forward_decoders(h, s, lb, h->cfg.huber);
+  return do_forward_decoders(h, s, lb, h->cfg.huber, recon16);
 }
 
-static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStream_t s, bool state_fused = false) {
+static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStream_t s, bool state_fused = false, bool recon16 = false) {
   MFVAE_TRY(check_ready(h, b));
   MFVAE_CHECK(loss_kind >= MFVAE_LOSS_DEFAULT && loss_kind <= MFVAE_LOSS_JOINT_MSE, "unknown loss kind");
   const int joint_mse = (loss_kind == MFVAE_LOSS_JOINT_MSE);
@@ -533,6 +537,7 @@ static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStre
   const double Bg = static_cast<double>(b->batch_global);
   ReconLossArgs a{};
   a.recon = reinterpret_cast<const float*>(h->ws + h->RS.off); a.recon_ld = h->RS.ld;
+  a.recon16 = recon16 ? reinterpret_cast<const __nv_bfloat16*>(h->ws + h->DRS.off) : nullptr;   // in place over D(recon_s)
   a.target = b->d_next; a.target_ld = h->S;
   a.grad = h->ws + h->DRS.off; a.grad_ld = h->DRS.ld; a.grad_dtype = h->dtype;
   a.B = h->B; a.width = h->S;
@@ -544,7 +549,7 @@ static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStre
   a.grad_scale = static_cast<float>(static_cast<double>(sw) / cs); a.loss_scale = static_cast<float>(1.0 / cs);
   a.loss_out = losses_ptr(h) + 1; a.scratch = scratch_ptr(h, 1);
   if (!state_fused) MFVAE_TRY(launch_recon_loss(a, s));
-  a.recon = reinterpret_cast<const float*>(h->ws + h->RR.off); a.recon_ld = h->RR.ld;
+  a.recon = reinterpret_cast<const float*>(h->ws + h->RR.off); a.recon_ld = h->RR.ld; a.recon16 = nullptr;
   a.target = b->d_rew; a.target_ld = h->A;
   a.grad = h->ws + h->DRR.off; a.grad_ld = h->DRR.ld; a.width = h->A;
   a.grad_scale = static_cast<float>(static_cast<double>(rw) / cr); a.loss_scale = static_cast<float>(1.0 / cr);
@@ -876,8 +881,11 @@ int mfvae_fwd_bwd(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* s
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // tensor-core engine: reconstruction loss of the state head fused into its output-layer GEMM (recon_s is not written)
   const bool fuse = h->use_tc && (h->cfg.fusion & MFVAE_FUSE_LOSS) && h->g_sout_loss >= 0 && b && b->d_next && b->d_rew;
-  MFVAE_TRY(do_forward(h, b, out, s, fuse));
-  MFVAE_TRY(do_loss(h, b, MFVAE_LOSS_DEFAULT, s, fuse));
+  // bf16 engine: the train step needs recon_s only inside the loss, so the output layer writes it once in bf16 straight into
+  // the D(recon_s) buffer and the loss kernel turns it into the gradient in place (no fp32 round trip: -140 MB per step)
+  const bool r16 = !fuse && h->use_tc && h->g_sout_fwd16 >= 0 && b && b->d_next && b->d_rew;
+  MFVAE_TRY(do_forward(h, b, out, s, fuse, r16));
+  MFVAE_TRY(do_loss(h, b, MFVAE_LOSS_DEFAULT, s, fuse, r16));
   return do_backward(h, b, s);
 }
 

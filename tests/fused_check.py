@@ -24,12 +24,13 @@ def main(latent, B, explicit_idx=False):
     dev = "cuda:0"
     spec = O.simple_tag_spec(latent=latent)
     models = {}
-    for fusion in ("none", "encoder+loss"):
+    for fusion in ("none", "encoder", "loss"):
         torch.manual_seed(7)
         m = M.MAVAE(spec.idx_features, spec.latent, spec.act_features, True, spec.agents, spec.obs_dim, spec.n_act, dev,
                     precision="bf16", fusion=fusion, include_dead_decoder=False)
         models[fusion] = m
-    models["encoder+loss"].load_named(models["none"].named_arena_tensors())
+    for k in ("encoder", "loss"):
+        models[k].load_named(models["none"].named_arena_tensors())
     g = torch.Generator(device=dev).manual_seed(11)
     S, A = spec.state_dim, spec.n_agents
     obs = torch.randn(B, S, device=dev, generator=g)
@@ -54,25 +55,29 @@ def main(latent, B, explicit_idx=False):
         grads = {k: p.grad.clone() for k, p in m.named_arena_tensors().items()}
         params = {k: p.detach().clone() for k, p in m.named_arena_tensors().items()}
         res[fusion] = (fw, losses, grads, params)
-    # fused loss epilogue (train_step) against the drop-in call sequence (forward -> loss -> backward: recon_s is
-    # materialised and the loss is its own kernel) on the same model and batch
-    m = models["encoder+loss"]
-    m.load_named(res["none"][3])
-    m.philox_step = 5
-    rs, rr, mus, lvs = m(M.PackedBatch(obs, act, idx=idx))
-    loss, sl, rl, kl = M.loss_s_r_vae_fn(rs, rr, nxt, rew, mus, lvs, dev)
-    loss.backward()
-    torch.cuda.synchronize()
-    g_drop = {k: p.grad.clone() for k, p in m.named_arena_tensors().items()}
-    l_drop = [float(loss), float(sl), float(rl), float(kl)]
-    m.philox_step = 5
-    l_fast = [float(x) for x in m.train_step(M.PackedBatch(obs, act, nxt, rew, idx=idx), 0.0).cpu()]
-    g_fast = {k: p.grad.clone() for k, p in m.named_arena_tensors().items()}
-    out["lossfuse_loss_rel"] = max(abs(a - b) / max(abs(b), 1e-30) for a, b in zip(l_fast, l_drop))
-    lf = {k: rel(g_fast[k], g_drop[k]) for k in g_fast}
-    out["lossfuse_grad_rel_max"] = max(lf.values())
-    out["lossfuse_grad_worst"] = max(lf, key=lf.get)
-    fa, la, ga, pa = res["encoder+loss"]
+    # train_step against the drop-in call sequence (forward -> loss -> backward: recon_s is materialised in fp32 and the
+    # loss is its own kernel) on the same model and batch:
+    #   "loss" model: the loss epilogue sees the same fp32 values as the separate kernel -> tight agreement
+    #   "none" model: train_step keeps recon_s only as bf16 inside the D(recon_s) buffer -> one more bf16 rounding point
+    for tag, key in (("lossfuse", "loss"), ("r16", "none")):
+        m = models[key]
+        m.load_named(res["none"][3])
+        m.philox_step = 5
+        rs, rr, mus, lvs = m(M.PackedBatch(obs, act, idx=idx))
+        loss, sl, rl, kl = M.loss_s_r_vae_fn(rs, rr, nxt, rew, mus, lvs, dev)
+        loss.backward()
+        torch.cuda.synchronize()
+        g_drop = {k: p.grad.clone() for k, p in m.named_arena_tensors().items()}
+        l_drop = [float(loss), float(sl), float(rl), float(kl)]
+        m.philox_step = 5
+        l_fast = [float(x) for x in m.train_step(M.PackedBatch(obs, act, nxt, rew, idx=idx), 0.0).cpu()]
+        g_fast = {k: p.grad.clone() for k, p in m.named_arena_tensors().items()}
+        out[tag + "_loss_rel"] = max(abs(a - b) / max(abs(b), 1e-30) for a, b in zip(l_fast, l_drop))
+        lf = {k: rel(g_fast[k], g_drop[k]) for k in g_fast}
+        out[tag + "_grad_rel_max"] = max(lf.values())
+        out[tag + "_grad_rel_median"] = sorted(lf.values())[len(lf) // 2]
+        out[tag + "_grad_worst"] = max(lf, key=lf.get)
+    fa, la, ga, pa = res["encoder"]
     fn, ln, gn, pn = res["none"]
     for k in fa:
         out["fwd_" + k] = rel(fa[k], fn[k])

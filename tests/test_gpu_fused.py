@@ -32,7 +32,9 @@ def test_fused_matches_layerwise(latent, batch, extra):
     assert max(o["fwd_rs"], o["fwd_rr"]) < 1e-4, o
     assert max(o["loss_rel"]) < 1e-4, o
     # gradients: split-K / atomic accumulation orders differ between the two schedules
-    assert o["grad_rel_median"] < 1e-3 and o["grad_rel_max"] < 2e-2, o
+    assert o["grad_rel_median"] < 1e-3 and o["grad_rel_max"] < 2e-2, (o["grad_rel_median"], o["grad_rel_worst"])
     # loss fused into the output-layer epilogue vs the separate loss kernel: same fp32 values enter the same formula
-    assert o["lossfuse_loss_rel"] < 1e-5, o
-    assert o["lossfuse_grad_rel_max"] < 1e-3, o
+    assert o["lossfuse_loss_rel"] < 1e-5 and o["lossfuse_grad_rel_max"] < 1e-3, {k: v for k, v in o.items() if k.startswith("lossfuse")}
+    # default train step: recon_s lives only as bf16 inside the D(recon_s) buffer (one extra bf16 rounding point)
+    assert o["r16_loss_rel"] < 1e-4 and o["r16_grad_rel_median"] < 2e-3 and o["r16_grad_rel_max"] < 1e-1, \
+        {k: v for k, v in o.items() if k.startswith("r16")}

@@ -233,18 +233,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // from here on global memory written by it is read
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  const long long tiles_per_split = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  // work index -> (group, split, m-tile, n-tile): 32-bit arithmetic (64-bit div / mod was 15 % of this kernel's instructions)
+  const uint32_t total_work = static_cast<uint32_t>(p.total_work);
+  const uint32_t n_tiles = static_cast<uint32_t>(p.n_tiles), m_tiles = static_cast<uint32_t>(p.m_tiles), n_splits = static_cast<uint32_t>(p.splits);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-        const int nt = static_cast<int>(w % p.n_tiles);
-        const int mt = static_cast<int>((w / p.n_tiles) % p.m_tiles);
-        const long long r = w / tiles_per_split;
-        const int ks = static_cast<int>(r % p.splits);
-        const int g = static_cast<int>(r / p.splits);
+      for (uint32_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const uint32_t q0 = w / n_tiles, q1 = q0 / m_tiles;
+        const int nt = static_cast<int>(w - q0 * n_tiles);
+        const int mt = static_cast<int>(q0 - q1 * m_tiles);
+        const uint32_t gq = q1 / n_splits;
+        const int ks = static_cast<int>(q1 - gq * n_splits);
+        const int g = static_cast<int>(gq);
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty + stage, phase ^ 1);
@@ -278,9 +281,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr uint32_t a_kstep = A_MN ? 2048u : 32u, b_kstep = B_MN ? 2048u : 32u;
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-        const long long r = w / tiles_per_split;
-        const int ks = static_cast<int>(r % p.splits);
+      for (uint32_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const uint32_t r = (w / n_tiles) / m_tiles;
+        const int ks = static_cast<int>(r % n_splits);
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
         mbar_wait(acc_empty + as, aphase ^ 1);
         tc_fence_after();
@@ -311,11 +314,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int half = (warp - 2) >> 2;              // which of the quarter's warps (0 .. kEpiWarps/4 - 1)
     int as = 0; uint32_t aphase = 0;
     float loss_acc = 0.f;
-    for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-      const int nt = static_cast<int>(w % p.n_tiles);
-      const int mt = static_cast<int>((w / p.n_tiles) % p.m_tiles);
-      const long long r = w / tiles_per_split;
-      const int g = static_cast<int>(r / p.splits);
+    for (uint32_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const uint32_t q0 = w / n_tiles, q1 = q0 / m_tiles;
+      const int nt = static_cast<int>(w - q0 * n_tiles);
+      const int mt = static_cast<int>(q0 - q1 * m_tiles);
+      const int g = static_cast<int>(q1 / n_splits);
       mbar_wait(acc_full + as, aphase);
       tc_fence_after();
       const int row = mt * BM + q * 32 + lane;
@@ -528,6 +531,7 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
   p.G = op.G; p.M = op.M; p.N = op.N; p.K = op.K;
   p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.k_blocks = k_blocks; p.splits = splits; p.kb_per_split = kb_per_split;
   p.total_work = static_cast<long long>(op.G) * splits * m_tiles * n_tiles;
+  if (p.total_work >= (1LL << 31)) { delete pl; MFVAE_FAIL("tcgen05 GEMM: too many tiles"); }
   p.C = op.C; p.c_gs = op.c_gs; p.c_ld = op.c_ld; p.c_dtype = op.c_dtype;
   p.bias = op.bias; p.bias_gs = op.bias_gs; p.epi = op.epi;
   p.aux = static_cast<const __nv_bfloat16*>(op.aux); p.aux_gs = op.aux_gs; p.aux_ld = op.aux_ld;

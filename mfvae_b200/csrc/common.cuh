@@ -138,17 +138,18 @@ constexpr int kTicketSlot = 4095;
 __device__ __forceinline__ void finish_scalar(float block_total, float* scratch, float scale, float* out,
                                               float* red) {
   __shared__ bool is_last;
+  const unsigned int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
   if (threadIdx.x == 0) {
-    scratch[blockIdx.x] = block_total;
+    scratch[bid] = block_total;
     __threadfence();
     unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(scratch + kTicketSlot), 1u);
-    is_last = (ticket == gridDim.x - 1);
+    is_last = (ticket == nblocks - 1);
   }
   __syncthreads();
   if (is_last) {
     __threadfence();
     float v = 0.f;
-    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += blockDim.x) v += __ldcg(scratch + i);
+    for (int i = threadIdx.x; i < static_cast<int>(nblocks); i += blockDim.x) v += __ldcg(scratch + i);
     v = block_sum(v, red);
     if (threadIdx.x == 0) {
       out[0] = v * scale;

@@ -157,37 +157,41 @@ int launch_stage(const StageArgs& a, cudaStream_t s, bool do_x0, bool do_act) {
 // 2 x 16-B loads (mu, logvar), one Philox4x32-10 call = 4 normals, one 16-B (fp32) / 8-B (bf16) store.
 // Algorithmic bytes per sample: 3 * A*L * 4 (fp32 z) = SURVEY 8(d).
 // ---------------------------------------------------------------------------------------------
-template <typename T, bool AGENT_MAJOR>
-__global__ void __launch_bounds__(kThreads) reparam_kl_fwd_kernel(ReparamArgs p) {
+// grid = (chunks, A): blockIdx.y is the agent, so the only index arithmetic per 4-element item is one 32-bit
+// shift (L / 4 a power of two) or division -- the integer bookkeeping used to outweigh the Philox rounds.
+__device__ __forceinline__ void split_item(uint32_t e, uint32_t lq, int lq_shift, uint32_t& b, uint32_t& jq) {
+  if (lq_shift >= 0) { b = e >> lq_shift; jq = e & (lq - 1); }
+  else               { b = e / lq; jq = e - b * lq; }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) reparam_kl_fwd_kernel(ReparamArgs p, uint32_t lq, int lq_shift, uint32_t items) {
   __shared__ float red[32];
-  const int lq = p.L / 4;
-  const int64_t total = p.B * p.A * lq;
-  T* z = static_cast<T*>(p.z);
+  const int a = blockIdx.y;
+  T* z = static_cast<T*>(p.z) + a * p.L;
+  const float* mu_a = p.mu + a * p.lat_as;
+  const float* lv_a = p.lv + a * p.lat_as;
+  const float* eps_a = p.eps ? p.eps + a * p.L : nullptr;
+  const uint32_t q0 = static_cast<uint32_t>(a * p.L) >> 2;           // Philox column-quad index of this agent's first column
   float acc = 0.f;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    // (sample, agent) pairs fit 32 bits (checked by the launcher): cheap unsigned division instead of 64-bit
-    const uint32_t pr = static_cast<uint32_t>(i / lq);
-    const int jq = static_cast<int>(i - static_cast<int64_t>(pr) * lq);
-    int a; int64_t b;
-    if (AGENT_MAJOR) { const uint32_t B32 = static_cast<uint32_t>(p.B); a = static_cast<int>(pr / B32); b = pr - static_cast<uint32_t>(a) * B32; }
-    else             { const uint32_t A32 = static_cast<uint32_t>(p.A); b = pr / A32; a = static_cast<int>(pr - static_cast<uint32_t>(b) * A32); }
-    const int64_t off = a * p.lat_as + b * p.lat_bs + jq * 4;
-    const float4 mu = ldg_stream4(p.mu + off);
-    const float4 lv = ldg_stream4(p.lv + off);
-    const int col = a * p.L + jq * 4;
-    float4 e;
-    if (p.eps) e = ldg_stream4(p.eps + b * p.eps_ld + col);
-    else       e = philox_normal4(p.seed, p.step, static_cast<uint64_t>(p.sample0 + b), static_cast<uint32_t>(col >> 2));
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < items; e += gridDim.x * blockDim.x) {
+    uint32_t b, jq;
+    split_item(e, lq, lq_shift, b, jq);
+    const int64_t off = static_cast<int64_t>(b) * p.lat_bs + jq * 4;
+    const float4 mu = ldg_stream4(mu_a + off);
+    const float4 lv = ldg_stream4(lv_a + off);
+    float4 ep;
+    if (eps_a) ep = ldg_stream4(eps_a + static_cast<int64_t>(b) * p.eps_ld + jq * 4);
+    else       ep = philox_normal4(p.seed, p.step, static_cast<uint64_t>(p.sample0 + b), q0 + jq);
     float4 o;
     // sigma = exp(lv / 2); exp(lv) = sigma^2 (one transcendental per element instead of two; 1 ulp apart)
     const float sx = expf(0.5f * lv.x), sy = expf(0.5f * lv.y), sz = expf(0.5f * lv.z), sw = expf(0.5f * lv.w);
     const float ex = sx * sx, ey = sy * sy, ez = sz * sz, ew = sw * sw;
-    o.x = mu.x + e.x * sx;
-    o.y = mu.y + e.y * sy;
-    o.z = mu.z + e.z * sz;
-    o.w = mu.w + e.w * sw;
-    store4<T>(z + b * p.z_ld + col, o);
+    o.x = mu.x + ep.x * sx;
+    o.y = mu.y + ep.y * sy;
+    o.z = mu.z + ep.z * sz;
+    o.w = mu.w + ep.w * sw;
+    store4<T>(z + static_cast<int64_t>(b) * p.z_ld + jq * 4, o);
     acc += (1.f + lv.x - mu.x * mu.x - ex) + (1.f + lv.y - mu.y * mu.y - ey) +
            (1.f + lv.z - mu.z * mu.z - ez) + (1.f + lv.w - mu.w * mu.w - ew);
   }
@@ -195,60 +199,65 @@ __global__ void __launch_bounds__(kThreads) reparam_kl_fwd_kernel(ReparamArgs p)
   finish_scalar(tot, p.scratch, -0.5f * p.kl_scale, p.kl_out, red);
 }
 
+static int reparam_grid(int64_t B, int A, int L, dim3* grid, uint32_t* lq, int* lq_shift, uint32_t* items) {
+  MFVAE_CHECK(B * (L / 4) < (1LL << 32), "reparam: batch * latent / 4 must fit 32 bits");
+  *lq = static_cast<uint32_t>(L / 4);
+  *lq_shift = -1;
+  for (int sft = 0; sft < 31; ++sft) if ((1u << sft) == *lq) *lq_shift = sft;
+  *items = static_cast<uint32_t>(B * (L / 4));
+  const int per_agent = std::max(1, std::min<int>(grid_for(*items), std::max(1, kNumSMs * 8 / A)));
+  MFVAE_CHECK(static_cast<int64_t>(per_agent) * A <= kMaxPartials, "reparam: too many blocks for the partial-sum scratch");
+  *grid = dim3(per_agent, A);
+  return 0;
+}
+
 int launch_reparam_kl_fwd(const ReparamArgs& a, cudaStream_t s) {
   MFVAE_CHECK(a.L % 4 == 0, "reparam: latent must be a multiple of 4");
   MFVAE_CHECK(a.lat_as % 4 == 0 && a.lat_bs % 4 == 0 && a.z_ld % 4 == 0, "reparam: strides must be multiples of 4");
-  MFVAE_CHECK(a.B * a.A < (1LL << 31), "reparam: batch * agents must fit 31 bits");
-  const int64_t total = a.B * a.A * (a.L / 4);
-  const int grid = grid_for(total);
-  const bool am = a.lat_as > a.lat_bs;
-  if (a.z_dtype == kBF16) {
-    if (am) reparam_kl_fwd_kernel<__nv_bfloat16, true><<<grid, kThreads, 0, s>>>(a);
-    else    reparam_kl_fwd_kernel<__nv_bfloat16, false><<<grid, kThreads, 0, s>>>(a);
-  } else {
-    if (am) reparam_kl_fwd_kernel<float, true><<<grid, kThreads, 0, s>>>(a);
-    else    reparam_kl_fwd_kernel<float, false><<<grid, kThreads, 0, s>>>(a);
-  }
+  MFVAE_CHECK(a.A <= 65535, "reparam: too many agents for one launch");
+  dim3 grid; uint32_t lq, items; int sh;
+  MFVAE_TRY(reparam_grid(a.B, a.A, a.L, &grid, &lq, &sh, &items));
+  if (a.z_dtype == kBF16) reparam_kl_fwd_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(a, lq, sh, items);
+  else                    reparam_kl_fwd_kernel<float><<<grid, kThreads, 0, s>>>(a, lq, sh, items);
   MFVAE_LAUNCH_CHECK();
   return 0;
 }
 
 template <typename TG, typename TD>
-__global__ void __launch_bounds__(kThreads) reparam_kl_bwd_kernel(ReparamBwdArgs p) {
-  const int lq = p.L / 4;
-  const int64_t total = p.B * p.A * lq;
-  const TG* gz = static_cast<const TG*>(p.gz);
-  TD* dl = static_cast<TD*>(p.dlat);
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const uint32_t pr = static_cast<uint32_t>(i / lq);
-    const int jq = static_cast<int>(i - static_cast<int64_t>(pr) * lq);
-    const uint32_t B32 = static_cast<uint32_t>(p.B);
-    const int a = static_cast<int>(pr / B32);
-    const int64_t b = pr - static_cast<uint32_t>(a) * B32;
-    const int64_t off = a * p.lat_as + b * p.lat_bs + jq * 4;
-    const float4 mu = *reinterpret_cast<const float4*>(p.mu + off);
-    const float4 lv = *reinterpret_cast<const float4*>(p.lv + off);
-    const int col = a * p.L + jq * 4;
-    const float4 g = load4<TG>(gz + b * p.gz_ld + col);
-    float4 e;
-    if (p.eps) e = *reinterpret_cast<const float4*>(p.eps + b * p.eps_ld + col);
-    else       e = philox_normal4(p.seed, p.step, static_cast<uint64_t>(p.sample0 + b), static_cast<uint32_t>(col >> 2));
-    const float k = p.kl_scale;
+__global__ void __launch_bounds__(kThreads) reparam_kl_bwd_kernel(ReparamBwdArgs p, uint32_t lq, int lq_shift, uint32_t items) {
+  const int a = blockIdx.y;
+  const TG* gz = static_cast<const TG*>(p.gz) + a * p.L;
+  TD* dl = static_cast<TD*>(p.dlat) + a * p.dlat_as;
+  const float* mu_a = p.mu + a * p.lat_as;
+  const float* lv_a = p.lv + a * p.lat_as;
+  const float* eps_a = p.eps ? p.eps + a * p.L : nullptr;
+  const float* glat_a = p.glat ? p.glat + a * p.lat_as : nullptr;
+  const uint32_t q0 = static_cast<uint32_t>(a * p.L) >> 2;
+  const float k = p.kl_scale;
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < items; e += gridDim.x * blockDim.x) {
+    uint32_t b, jq;
+    split_item(e, lq, lq_shift, b, jq);
+    const int64_t off = static_cast<int64_t>(b) * p.lat_bs + jq * 4;
+    const float4 mu = *reinterpret_cast<const float4*>(mu_a + off);
+    const float4 lv = *reinterpret_cast<const float4*>(lv_a + off);
+    const float4 g = load4<TG>(gz + static_cast<int64_t>(b) * p.gz_ld + jq * 4);
+    float4 ep;
+    if (eps_a) ep = *reinterpret_cast<const float4*>(eps_a + static_cast<int64_t>(b) * p.eps_ld + jq * 4);
+    else       ep = philox_normal4(p.seed, p.step, static_cast<uint64_t>(p.sample0 + b), q0 + jq);
     float4 dmu, dlv;
     dmu.x = g.x + k * mu.x; dmu.y = g.y + k * mu.y; dmu.z = g.z + k * mu.z; dmu.w = g.w + k * mu.w;
     const float sx = expf(0.5f * lv.x), sy = expf(0.5f * lv.y), sz = expf(0.5f * lv.z), sw = expf(0.5f * lv.w);
-    dlv.x = g.x * e.x * 0.5f * sx + k * 0.5f * (sx * sx - 1.f);
-    dlv.y = g.y * e.y * 0.5f * sy + k * 0.5f * (sy * sy - 1.f);
-    dlv.z = g.z * e.z * 0.5f * sz + k * 0.5f * (sz * sz - 1.f);
-    dlv.w = g.w * e.w * 0.5f * sw + k * 0.5f * (sw * sw - 1.f);
-    if (p.glat) {
-      const float4 um = *reinterpret_cast<const float4*>(p.glat + off);
-      const float4 ul = *reinterpret_cast<const float4*>(p.glat + off + p.L);
+    dlv.x = g.x * ep.x * 0.5f * sx + k * 0.5f * (sx * sx - 1.f);
+    dlv.y = g.y * ep.y * 0.5f * sy + k * 0.5f * (sy * sy - 1.f);
+    dlv.z = g.z * ep.z * 0.5f * sz + k * 0.5f * (sz * sz - 1.f);
+    dlv.w = g.w * ep.w * 0.5f * sw + k * 0.5f * (sw * sw - 1.f);
+    if (glat_a) {
+      const float4 um = *reinterpret_cast<const float4*>(glat_a + off);
+      const float4 ul = *reinterpret_cast<const float4*>(glat_a + off + p.L);
       dmu.x += um.x; dmu.y += um.y; dmu.z += um.z; dmu.w += um.w;
       dlv.x += ul.x; dlv.y += ul.y; dlv.z += ul.z; dlv.w += ul.w;
     }
-    TD* o = dl + a * p.dlat_as + b * p.dlat_bs + jq * 4;
+    TD* o = dl + static_cast<int64_t>(b) * p.dlat_bs + jq * 4;
     store4<TD>(o, dmu);
     store4<TD>(o + p.L, dlv);
   }
@@ -257,10 +266,11 @@ __global__ void __launch_bounds__(kThreads) reparam_kl_bwd_kernel(ReparamBwdArgs
 int launch_reparam_kl_bwd(const ReparamBwdArgs& a, cudaStream_t s) {
   MFVAE_CHECK(a.L % 4 == 0 && a.gz_ld % 4 == 0 && a.dlat_bs % 4 == 0, "reparam bwd: widths must be multiples of 4");
   MFVAE_CHECK(a.g_dtype == a.d_dtype, "reparam bwd: mixed dtypes unsupported");
-  MFVAE_CHECK(a.B * a.A < (1LL << 31), "reparam bwd: batch * agents must fit 31 bits");
-  const int grid = grid_for(a.B * a.A * (a.L / 4));
-  if (a.g_dtype == kBF16) reparam_kl_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kThreads, 0, s>>>(a);
-  else                    reparam_kl_bwd_kernel<float, float><<<grid, kThreads, 0, s>>>(a);
+  MFVAE_CHECK(a.A <= 65535, "reparam bwd: too many agents for one launch");
+  dim3 grid; uint32_t lq, items; int sh;
+  MFVAE_TRY(reparam_grid(a.B, a.A, a.L, &grid, &lq, &sh, &items));
+  if (a.g_dtype == kBF16) reparam_kl_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kThreads, 0, s>>>(a, lq, sh, items);
+  else                    reparam_kl_bwd_kernel<float, float><<<grid, kThreads, 0, s>>>(a, lq, sh, items);
   MFVAE_LAUNCH_CHECK();
   return 0;
 }

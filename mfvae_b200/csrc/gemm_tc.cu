@@ -76,9 +76,11 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row
     const float* b = p.bias + g * p.bias_gs + col0;
     if (ncols == 32) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < 32; j += 4) {       // packed fp32x2 adds (sm_100): half the issue slots of 32 scalar FADDs
         const float4 bb = __ldg(reinterpret_cast<const float4*>(b + j));
-        f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+        const float2 s0 = __fadd2_rn(make_float2(f[j], f[j + 1]), make_float2(bb.x, bb.y));
+        const float2 s1 = __fadd2_rn(make_float2(f[j + 2], f[j + 3]), make_float2(bb.z, bb.w));
+        f[j] = s0.x; f[j + 1] = s0.y; f[j + 2] = s1.x; f[j + 3] = s1.y;
       }
     } else {
 #pragma unroll

@@ -91,3 +91,36 @@ def test_ring_fed_train_steps_match_host_fed():
     host = M.PackedBatch(take[:, :S].cuda(), take[:, S:S + A].cuda(), take[:, S + A:2 * S + A].cuda(), take[:, 2 * S + A:2 * S + 2 * A].cuda())
     b = m.test_step(host).clone()
     assert torch.equal(a, b)
+
+
+def test_full_size_shard_additivity_and_determinism():
+    """Size-independent properties at the benchmark's full size (cfg2: 40 agents, B = 4096, bf16 / tcgen05): the
+    gradients of two half-batch shards (scaled by the global batch, Philox keyed by the global sample index) add up to
+    the full-batch gradients, and the loss scalars are bit-reproducible run to run."""
+    import mfvae_b200 as M
+    from oracle import mavae_oracle as O
+    spec = O.simple_tag_spec(latent=32)
+    torch.manual_seed(3)
+    m = M.MAVAE(spec.idx_features, spec.latent, spec.act_features, True, spec.agents, spec.obs_dim, spec.n_act, "cuda:0",
+                precision="bf16", include_dead_decoder=False)
+    B = 4096
+    pb = _batch(M, spec, B, seed=21)
+
+    def run(lo, hi):
+        m.philox_step = 0
+        part = M.PackedBatch(pb.obs[lo:hi].contiguous(), pb.act[lo:hi].contiguous(), pb.next[lo:hi].contiguous(),
+                             pb.rew[lo:hi].contiguous(), sample0=lo, batch_global=B)
+        losses = m.train_step(part, 0.0).clone()
+        return losses, m._grad.clone()
+
+    l_full, g_full = run(0, B)
+    l_again, _ = run(0, B)
+    assert torch.equal(l_full, l_again)                       # fixed-order reductions: bit-identical scalars
+    l0, g0 = run(0, B // 2)
+    l1, g1 = run(B // 2, B)
+    assert torch.allclose(l0 + l1, l_full, rtol=2e-5)
+    n = m._n_opt
+    # same per-sample bf16 rounding points in both schedules: only fp32 accumulation order differs
+    for lo, hi, what in ((0, n, "optimised prefix"), (n, g_full.numel(), "encoders / action tables")):
+        d = float((g0[lo:hi] + g1[lo:hi] - g_full[lo:hi]).norm() / g_full[lo:hi].norm())
+        assert d < 2e-4, (what, d)

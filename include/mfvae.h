@@ -163,6 +163,9 @@ int mfvae_adam_step_overlapped(MfvaeHandle h, float lr, float beta1, float beta2
 int mfvae_adam_range(MfvaeHandle h, int64_t begin, int64_t end, float lr, float beta1, float beta2, float eps, int64_t t,
                      void* stream);
 int mfvae_wait_decoder_reads(MfvaeHandle h, void* stream);
+/* persistent GEMM grids use (148 - n_sms) SMs, leaving room for the collective's kernels that run beside backward: a
+ * persistent kernel whose CTAs cannot all be resident at once runs a second wave (process-wide setting) */
+int mfvae_set_sm_reserve(MfvaeHandle h, int32_t n_sms);
 /* forward + loss + backward in one call (no optimizer; the host all-reduces gradients in between).  With the bf16 /
  * tcgen05 engine the state reconstruction is consumed by the loss without an fp32 copy in HBM: out->d_recon_s is NULL
  * (d_recon_r, d_latent and d_losses are valid); call mfvae_forward when recon_s itself is wanted. */

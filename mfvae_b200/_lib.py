@@ -79,6 +79,7 @@ SIGNATURES = {
     "mfvae_adam_step_overlapped": (C.c_int, [_vp, _f, _f, _f, _f, _i64, _vp]),
     "mfvae_adam_range": (C.c_int, [_vp, _i64, _i64, _f, _f, _f, _f, _i64, _vp]),
     "mfvae_wait_decoder_reads": (C.c_int, [_vp, _vp]),
+    "mfvae_set_sm_reserve": (C.c_int, [_vp, _i32]),
     "mfvae_fwd_bwd": (C.c_int, [_vp, C.POINTER(MfvaeBatch), C.POINTER(MfvaeOutputs), _vp]),
     "mfvae_launch_count": (C.c_uint64, []),
     "mfvae_profile_enable": (C.c_int, [_vp, _i32]),

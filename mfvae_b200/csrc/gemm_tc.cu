@@ -27,6 +27,10 @@
 
 namespace mfvae {
 
+// SMs left free for a concurrently running collective (data parallel): persistent GEMMs whose CTAs cannot all be resident
+// at once run a second wave -- see mfvae_set_sm_reserve
+int g_tc_sm_reserve = 0;
+
 constexpr int BM = 128;
 constexpr int BK = 64;                    // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 // Two launch shapes.  CPS = CTAs per SM:
@@ -540,7 +544,7 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
   p.tgt = nullptr; p.tgt_ld = 0; p.grad_scale = 0.f; p.huber = 1; p.loss_partials = nullptr;
   p.accumulate_atomic = (op.epi == kEpiAccum && splits > 1) ? 1 : 0;   // single split: plain stores into the zeroed C
   pl->BN = BN;
-  pl->grid = static_cast<int>(std::min<long long>(p.total_work, static_cast<long long>(kNumSMs) * pl->cps));
+  pl->grid = static_cast<int>(std::min<long long>(p.total_work, static_cast<long long>(kNumSMs - g_tc_sm_reserve) * pl->cps));
   int rc = encode_operand(&pl->map_a, op.A, op.M, op.K, op.G, op.a_gs, op.a_rs, op.a_cs, BM, &pl->a_mn);
   if (rc == 0) rc = encode_operand(&pl->map_b, op.B, op.N, op.K, op.G, op.b_gs, op.b_rs, op.b_cs, BN, &pl->b_mn);
   if (rc != 0) { delete pl; return rc; }

@@ -109,6 +109,7 @@ struct GemmOp {
 int gemm_simt(const GemmOp& op, cudaStream_t s);
 
 // tcgen05 path: tensor maps are built once per op (plan time) and reused every step.
+extern int g_tc_sm_reserve;                             // SMs the persistent GEMM grids leave to concurrent collectives
 struct TcPlan;
 int gemm_tc_plan(const GemmOp& op, TcPlan** out);       // validates alignment, encodes CUtensorMaps
 int gemm_tc_run(const TcPlan* p, cudaStream_t s);

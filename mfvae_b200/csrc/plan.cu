@@ -640,6 +640,8 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
   MFVAE_TRY(csum_into_w());
   MFVAE_CUDA(cudaEventRecord(h->buckets[0].ev, w));
   // decoder hidden layers, last to first
+  // (a high-priority stream of its own for layer 0's wgrad -- the largest bucket -- was measured: no change at 1 or 2 GPUs;
+  //  the persistent GEMM CTAs already resident decide the order, not the stream priority)
   for (int l = nh - 1; l >= 0; --l) {
     MFVAE_TRY(fork());                                          // D_l (both decoder halves) ready
     MFVAE_TRY(run_gemm(h, h->g_dec_wg[l], w));
@@ -752,7 +754,6 @@ int mfvae_create(const MfvaeConfig* cfg, int device, MfvaeHandle* out) {
   cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming);
   if (cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess) h->aux = nullptr;
   if (cudaStreamCreateWithFlags(&h->csum, cudaStreamNonBlocking) != cudaSuccess) h->csum = nullptr;
-  for (int i = 0; i < 6; ++i) { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); h->csum_ev.push_back(e); }
   cudaEventCreateWithFlags(&h->aux_fork_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->aux_join_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->aux_fork2_ev, cudaEventDisableTiming);
@@ -933,6 +934,15 @@ int mfvae_adam_range(MfvaeHandle h, int64_t begin, int64_t end, float lr, float 
 int mfvae_wait_decoder_reads(MfvaeHandle h, void* stream) {
   MFVAE_CHECK(h && h->dec_read_ev, "no backward pass has been recorded");
   MFVAE_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->dec_read_ev, 0));
+  return 0;
+}
+
+// Persistent GEMM grids leave `n_sms` SMs unclaimed (process-wide; takes effect for plans built afterwards: the handle's
+// plans are rebuilt here).  Data parallel sets it to the number of SMs the NCCL kernels occupy.
+int mfvae_set_sm_reserve(MfvaeHandle h, int32_t n_sms) {
+  MFVAE_CHECK(n_sms >= 0 && n_sms < kNumSMs / 2, "sm reserve out of range");
+  g_tc_sm_reserve = n_sms;
+  if (h && h->ws && h->ar.d_param) return build_ops(h);
   return 0;
 }
 

@@ -31,6 +31,9 @@ from . import _lib as L
 kl_weight = 0.0025
 r_weight = 0.005
 
+import os as _os
+_DP_DEBUG = _os.environ.get("MFVAE_DP_DEBUG", "")     # "nocomm" / "noloss": scaling-loss attribution experiments only
+
 _ENC_HIDDEN = (64, 64, 256)
 _DEC_HIDDEN = (1024, 256, 64, 256, 1024)
 
@@ -555,6 +558,12 @@ class MAVAE(nn.Module):
         self.data_parallel = dist.get_world_size(process_group) > 1
         if self._on_gpu and self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(self._tdev)
+        if self._on_gpu and self.data_parallel:
+            # SMs the persistent GEMM grids leave to the NCCL kernels running beside backward.  Measured at 2 GPUs: 0 / 16 / 32
+            # reserved -> 1.091 / 1.084 / 1.113 ms per step (NCCL's CTAs co-reside with ours), so the default is 0.
+            reserve = int(_os.environ.get("MFVAE_SM_RESERVE", "0"))
+            L.check(L.lib().mfvae_set_sm_reserve(self._h, reserve))
+            self._ws_batch = -1 if self._ws is None else self._ws_batch
 
     def grad_buckets(self):
         lib = L.lib()
@@ -587,10 +596,12 @@ class MAVAE(nn.Module):
         if adam is not None:
             self._adam_t += 1
         guarded = False
+        dbg = _DP_DEBUG            # measurement switches (MFVAE_DP_DEBUG): never set in production
         with torch.cuda.stream(cs):
             for i, b, e in buckets:
                 L.check(lib.mfvae_bucket_wait(self._h, i, csp))
-                dist.all_reduce(self._grad[b:e], group=self._pg, async_op=True).wait()     # cs waits for NCCL
+                if "nocomm" not in dbg:
+                    dist.all_reduce(self._grad[b:e], group=self._pg, async_op=True).wait()     # cs waits for NCCL
                 if adam is not None:
                     if not guarded:     # backward may still be reading the decoder weights these buckets hold
                         L.check(lib.mfvae_wait_decoder_reads(self._h, csp))
@@ -599,7 +610,8 @@ class MAVAE(nn.Module):
                     L.check(lib.mfvae_adam_range(self._h, b, min(e, self._n_opt), float(lr), float(betas[0]), float(betas[1]),
                                                  float(eps), self._adam_t, csp))
             cs.wait_stream(main)       # losses are final at the end of the main stream's queue
-            dist.all_reduce(self._losses, group=self._pg, async_op=True).wait()
+            if "nocomm" not in dbg and "noloss" not in dbg:
+                dist.all_reduce(self._losses, group=self._pg, async_op=True).wait()
         main.wait_stream(cs)
 
     def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, overlapped=False):

@@ -590,14 +590,14 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, c
 }
 
 int launch_adam(float* p, const float* g, float* m, float* v, __nv_bfloat16* shadow, int64_t n,
-                float lr, float b1, float b2, float eps, int64_t t, cudaStream_t s) {
+                float lr, float b1, float b2, float eps, int64_t t, cudaStream_t s, int blocks_per_sm) {
   MFVAE_CHECK(n % 4 == 0, "adam: element count must be a multiple of 4");
   MFVAE_CHECK(t >= 1, "adam: step count starts at 1");
   const double bc1 = 1.0 - pow(static_cast<double>(b1), static_cast<double>(t));
   const double bc2 = 1.0 - pow(static_cast<double>(b2), static_cast<double>(t));
   const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
   const float bc2_sqrt = static_cast<float>(sqrt(bc2));
-  adam_kernel<<<grid_for(n / 4), kThreads, 0, s>>>(p, g, m, v, shadow, n / 4, 1.f - b1, b2, 1.f - b2,
+  adam_kernel<<<grid_for(n / 4, blocks_per_sm), kThreads, 0, s>>>(p, g, m, v, shadow, n / 4, 1.f - b1, b2, 1.f - b2,
                                                   step_size, bc2_sqrt, eps);
   MFVAE_LAUNCH_CHECK();
   return 0;

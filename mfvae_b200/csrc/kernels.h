@@ -81,7 +81,7 @@ int launch_stage_actions(const float* act, int64_t act_ld, const int32_t* act_of
                          int A, int64_t B, int Kap, cudaStream_t s);
 
 int launch_adam(float* p, const float* g, float* m, float* v, __nv_bfloat16* shadow, int64_t n,
-                float lr, float b1, float b2, float eps, int64_t t, cudaStream_t s);
+                float lr, float b1, float b2, float eps, int64_t t, cudaStream_t s, int blocks_per_sm = 8);
 // dst[b][c] = src[b][c] for c < width (fp32 -> activation dtype); src == nullptr writes zeros
 int launch_cast2d(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int dtype, int64_t B, int width, cudaStream_t s);
 int launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t s);

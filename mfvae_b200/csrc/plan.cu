@@ -84,6 +84,8 @@ struct MfvaeHandle_ {
   cudaEvent_t join_ev = nullptr;
   // third stream: the reward head (two tiny GEMM chains) and the action-embedding kernels run beside the big layers
   cudaStream_t aux = nullptr;
+  bool grads_zeroed = false;                 // mfvae_fwd_bwd: the gradient arena was zeroed on csum beside the forward pass
+  cudaEvent_t zero_ev = nullptr, zero_fork_ev = nullptr;
   cudaStream_t csum = nullptr;               // fourth stream: the bias column sums (HBM-bound) run beside the wgrad GEMMs
   std::vector<cudaEvent_t> csum_ev;
   cudaEvent_t aux_fork_ev = nullptr, aux_join_ev = nullptr, aux_fork2_ev = nullptr, aux_join2_ev = nullptr;
@@ -456,17 +458,22 @@ static int do_forward_act_embed(MfvaeHandle_* h, const StageArgs& st, cudaStream
 
 // loss_batch != nullptr (train step): the state output layer runs with the loss epilogue -- recon_s is not materialised,
 // D(recon_s) and the per-warp loss partials come straight out of the GEMM (the target must be bound in the batch).
-static int do_forward_decoders(MfvaeHandle_* h, cudaStream_t s, const MfvaeBatch* loss_batch = nullptr, int huber = 1, bool recon16 = false) {
+static int do_forward_decoders(MfvaeHandle_* h, cudaStream_t s, const MfvaeBatch* loss_batch = nullptr, int huber = 1, bool recon16 = false,
+                               bool defer_reward_join = false) {
   const bool aux = use_aux(h);
   if (aux) MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join_ev, 0));     // action embeddings are in ZIN
   for (int l = 0; l < h->cfg.n_dec_hidden; ++l) MFVAE_TRY(run_gemm(h, h->g_dec_fwd[l], s));
-  // reward head (two tiny GEMMs) beside the state output layer
+  // reward head (two tiny GEMMs) beside the state output layer.  It is enqueued FIRST: the output layer is a persistent
+  // kernel that claims every SM for ~50 us, and whatever is launched behind it starves until it retires.
   cudaStream_t r = s;
   if (aux) {
     MFVAE_CUDA(cudaEventRecord(h->aux_fork2_ev, s));
     MFVAE_CUDA(cudaStreamWaitEvent(h->aux, h->aux_fork2_ev, 0));
     r = h->aux;
   }
+  MFVAE_TRY(run_gemm(h, h->g_rout_fwd, r));
+  MFVAE_TRY(run_gemm(h, h->g_rl_fwd, r));
+  if (aux) MFVAE_CUDA(cudaEventRecord(h->aux_join2_ev, h->aux));
   if (loss_batch) {
     const double cs = static_cast<double>(loss_batch->batch_global) * h->S;
     MFVAE_TRY(gemm_tc_set_loss(h->tc[h->g_sout_loss], loss_batch->d_next, h->S, static_cast<float>(static_cast<double>(h->s_weight) / cs), huber,
@@ -477,16 +484,12 @@ static int do_forward_decoders(MfvaeHandle_* h, cudaStream_t s, const MfvaeBatch
   } else {
     MFVAE_TRY(run_gemm(h, h->g_sout_fwd, s));
   }
-  MFVAE_TRY(run_gemm(h, h->g_rout_fwd, r));
-  MFVAE_TRY(run_gemm(h, h->g_rl_fwd, r));
-  if (aux) {
-    MFVAE_CUDA(cudaEventRecord(h->aux_join2_ev, h->aux));
-    MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join2_ev, 0));
-  }
+  if (aux && !defer_reward_join) MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join2_ev, 0));
   return 0;
 }
 
-static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, cudaStream_t s, bool fuse_loss = false, bool recon16 = false) {
+static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, cudaStream_t s, bool fuse_loss = false, bool recon16 = false,
+                      bool defer_reward_join = false) {
   MFVAE_TRY(check_ready(h, b));
   const MfvaeBatch* lb = fuse_loss ? b : nullptr;
   StageArgs st{};
@@ -512,7 +515,7 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
     eb.eps = b->d_eps; eb.eps_ld = static_cast<int64_t>(h->A) * h->L; eb.seed = b->seed; eb.step = b->step; eb.sample0 = b->sample0;
     eb.kl_scale = 1.0f / static_cast<float>(b->batch_global); eb.kl_out = losses_ptr(h) + 3; eb.scratch = scratch_ptr(h, 0);
     MFVAE_TRY(enc_fused_forward(h->enc_fused, eb, s));
-    return do_forward_decoders(h, s, lb, h->cfg.huber, recon16);
+    return do_forward_decoders(h, s, lb, h->cfg.huber, recon16, defer_reward_join);
   }
   MFVAE_TRY(do_forward_act_embed(h, st, s));
   MFVAE_TRY(launch_stage(st, s, true, false));
@@ -525,10 +528,11 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
   rp.kl_scale = 1.0f / static_cast<float>(b->batch_global);
   rp.kl_out = losses_ptr(h) + 3; rp.scratch = scratch_ptr(h, 0);
   MFVAE_TRY(launch_reparam_kl_fwd(rp, s));
-  return do_forward_decoders(h, s, lb, h->cfg.huber, recon16);
+  return do_forward_decoders(h, s, lb, h->cfg.huber, recon16, defer_reward_join);
 }
 
-static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStream_t s, bool state_fused = false, bool recon16 = false) {
+static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStream_t s, bool state_fused = false, bool recon16 = false,
+                   bool join_reward = false) {
   MFVAE_TRY(check_ready(h, b));
   MFVAE_CHECK(loss_kind >= MFVAE_LOSS_DEFAULT && loss_kind <= MFVAE_LOSS_JOINT_MSE, "unknown loss kind");
   const int joint_mse = (loss_kind == MFVAE_LOSS_JOINT_MSE);
@@ -549,6 +553,7 @@ static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStre
   a.grad_scale = static_cast<float>(static_cast<double>(sw) / cs); a.loss_scale = static_cast<float>(1.0 / cs);
   a.loss_out = losses_ptr(h) + 1; a.scratch = scratch_ptr(h, 1);
   if (!state_fused) MFVAE_TRY(launch_recon_loss(a, s));
+  if (join_reward && use_aux(h)) MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join2_ev, 0));   // reward head (aux stream) is needed from here
   a.recon = reinterpret_cast<const float*>(h->ws + h->RR.off); a.recon_ld = h->RR.ld; a.recon16 = nullptr;
   a.target = b->d_rew; a.target_ld = h->A;
   a.grad = h->ws + h->DRR.off; a.grad_ld = h->DRR.ld; a.width = h->A;
@@ -560,6 +565,23 @@ static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStre
                                 static_cast<float>(1.0 / cs)));
   else
     MFVAE_TRY(launch_loss_total(losses_ptr(h), sw, rw, h->cfg.kl_weight, s));
+  return 0;
+}
+
+// optimizer.zero_grad(): split-K wgrads and bias column sums accumulate with fp32 atomics.  The two largest weight
+// gradients (decoder layer 0, state output layer) are written by single-split wgrads with plain stores and are
+// skipped (they are 2/3 of the arena).
+static int zero_grads(MfvaeHandle_* h, cudaStream_t q) {
+  float* G = h->ar.d_grad;
+  int64_t skip[2][2]; int ns = 0;
+  if (h->use_tc && gemm_tc_overwrites(h->tc[h->g_dec_wg[0]])) { skip[ns][0] = h->decW[0].off; skip[ns][1] = h->decB[0].off; ++ns; }
+  if (h->use_tc && gemm_tc_overwrites(h->tc[h->g_sout_wg])) { skip[ns][0] = h->sOutW.off; skip[ns][1] = h->sOutB.off; ++ns; }
+  int64_t cur = 0;
+  for (int i = 0; i <= ns; ++i) {
+    const int64_t end = (i < ns) ? skip[i][0] : h->arena_elems;
+    if (end > cur) MFVAE_CUDA(cudaMemsetAsync(G + cur, 0, static_cast<size_t>(end - cur) * sizeof(float), q));
+    if (i < ns) cur = skip[i][1];
+  }
   return 0;
 }
 
@@ -595,20 +617,9 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
     ++cs_i;
     return 0;
   };
-  // optimizer.zero_grad(): split-K wgrads and bias column sums accumulate with fp32 atomics.  The two largest weight
-  // gradients (decoder layer 0, state output layer) are written by single-split wgrads with plain stores and are
-  // skipped (they are 2/3 of the arena).
-  {
-    int64_t skip[2][2]; int ns = 0;
-    if (h->use_tc && gemm_tc_overwrites(h->tc[h->g_dec_wg[0]])) { skip[ns][0] = h->decW[0].off; skip[ns][1] = h->decB[0].off; ++ns; }
-    if (h->use_tc && gemm_tc_overwrites(h->tc[h->g_sout_wg])) { skip[ns][0] = h->sOutW.off; skip[ns][1] = h->sOutB.off; ++ns; }
-    int64_t cur = 0;
-    for (int i = 0; i <= ns; ++i) {
-      const int64_t end = (i < ns) ? skip[i][0] : h->arena_elems;
-      if (end > cur) MFVAE_CUDA(cudaMemsetAsync(G + cur, 0, static_cast<size_t>(end - cur) * sizeof(float), s));
-      if (i < ns) cur = skip[i][1];
-    }
-  }
+  if (!h->grads_zeroed) MFVAE_TRY(zero_grads(h, s));            // (mfvae_fwd_bwd zeroes them beside the forward pass)
+  else MFVAE_CUDA(cudaStreamWaitEvent(s, h->zero_ev, 0));
+  h->grads_zeroed = false;
   MFVAE_TRY(fork());                                            // D(recon_s), D(recon_r) and the zeroed arena are ready
   // reward head: reward_linear and the reward decoder's output layer are tiny; their whole backward chain runs on the
   // aux stream beside the state output layer (which owns the SMs for ~70 us on each of the other two streams)
@@ -618,12 +629,14 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
     MFVAE_CUDA(cudaEventRecord(h->aux_fork_ev, s));
     MFVAE_CUDA(cudaStreamWaitEvent(h->aux, h->aux_fork_ev, 0));
   }
-  // output layers + reward_linear
-  MFVAE_TRY(run_gemm(h, h->g_sout_wg, w));
-  MFVAE_TRY(launch_colsum(ws + h->DRS.off, dt, 1, h->B, h->S, h->DRS.ld, 0, G + h->sOutB.off, 0, cs));
-  MFVAE_TRY(run_gemm(h, h->g_sout_dg, s));
+  // reward-head dgrads first (aux): the two output-layer GEMMs below are persistent kernels that claim every SM, and the
+  // decoder dgrad chain on the caller's stream needs the reward half of D before it can go on
   MFVAE_TRY(run_gemm(h, h->g_rl_dg, r));
   MFVAE_TRY(run_gemm(h, h->g_rout_dg, r));
+  // output layers
+  MFVAE_TRY(run_gemm(h, h->g_sout_dg, s));
+  MFVAE_TRY(run_gemm(h, h->g_sout_wg, w));
+  MFVAE_TRY(launch_colsum(ws + h->DRS.off, dt, 1, h->B, h->S, h->DRS.ld, 0, G + h->sOutB.off, 0, cs));
   if (auxo) {                                                   // D of the last hidden layer: state half (s) + reward half (aux)
     MFVAE_CUDA(cudaEventRecord(h->aux_join_ev, h->aux));
     MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join_ev, 0));
@@ -754,6 +767,9 @@ int mfvae_create(const MfvaeConfig* cfg, int device, MfvaeHandle* out) {
   cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming);
   if (cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess) h->aux = nullptr;
   if (cudaStreamCreateWithFlags(&h->csum, cudaStreamNonBlocking) != cudaSuccess) h->csum = nullptr;
+  for (int i = 0; i < 6; ++i) { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); h->csum_ev.push_back(e); }
+  cudaEventCreateWithFlags(&h->zero_ev, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->zero_fork_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->aux_fork_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->aux_join_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->aux_fork2_ev, cudaEventDisableTiming);
@@ -784,6 +800,8 @@ int mfvae_destroy(MfvaeHandle h) {
   if (h->side) cudaStreamDestroy(h->side);
   if (h->aux) cudaStreamDestroy(h->aux);
   if (h->csum) cudaStreamDestroy(h->csum);
+  if (h->zero_ev) cudaEventDestroy(h->zero_ev);
+  if (h->zero_fork_ev) cudaEventDestroy(h->zero_fork_ev);
   for (auto e : h->csum_ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {h->aux_fork_ev, h->aux_join_ev, h->aux_fork2_ev, h->aux_join2_ev}) if (e) cudaEventDestroy(e);
   if (h->opt_ev) cudaEventDestroy(h->opt_ev);
@@ -885,8 +903,17 @@ int mfvae_fwd_bwd(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* s
   // bf16 engine: the train step needs recon_s only inside the loss, so the output layer writes it once in bf16 straight into
   // the D(recon_s) buffer and the loss kernel turns it into the gradient in place (no fp32 round trip: -140 MB per step)
   const bool r16 = !fuse && h->use_tc && h->g_sout_fwd16 >= 0 && b && b->d_next && b->d_rew;
-  MFVAE_TRY(do_forward(h, b, out, s, fuse, r16));
-  MFVAE_TRY(do_loss(h, b, MFVAE_LOSS_DEFAULT, s, fuse, r16));
+  if (h->csum && !h->profiling) {
+    // zero_grad beside the forward pass: ordered after everything already queued on the caller's stream (the previous
+    // optimizer step read these gradients), awaited by backward
+    MFVAE_CUDA(cudaEventRecord(h->zero_fork_ev, s));
+    MFVAE_CUDA(cudaStreamWaitEvent(h->csum, h->zero_fork_ev, 0));
+    MFVAE_TRY(zero_grads(h, h->csum));
+    MFVAE_CUDA(cudaEventRecord(h->zero_ev, h->csum));
+    h->grads_zeroed = true;
+  }
+  MFVAE_TRY(do_forward(h, b, out, s, fuse, r16, true));
+  MFVAE_TRY(do_loss(h, b, MFVAE_LOSS_DEFAULT, s, fuse, r16, true));
   return do_backward(h, b, s);
 }
 
@@ -907,8 +934,9 @@ int mfvae_adam_step_overlapped(MfvaeHandle h, float lr, float beta1, float beta2
   __nv_bfloat16* sh = static_cast<__nv_bfloat16*>(h->ar.d_shadow_bf16);
   auto range = [&](int64_t b, int64_t e, cudaStream_t st) -> int {
     if (e <= b) return 0;
+    // 4 blocks per SM when it runs beside the wgrad tail: 8 x 256 threads would take every thread slot of the SM
     return launch_adam(h->ar.d_param + b, h->ar.d_grad + b, h->ar.d_m + b, h->ar.d_v + b, sh ? sh + b : nullptr, e - b,
-                       lr, beta1, beta2, eps, t, st);
+                       lr, beta1, beta2, eps, t, st, st == s ? 8 : 4);
   };
   for (int i = 0; i < 3; ++i) MFVAE_CUDA(cudaStreamWaitEvent(h->opt_stream, h->buckets[i].ev, 0));
   MFVAE_CUDA(cudaStreamWaitEvent(h->opt_stream, h->dec_read_ev, 0));    // the dgrad chain has finished reading the decoder weights

@@ -12,6 +12,7 @@
 //     RS[B][Sp](fp32) RR0[B][Ap] RR[B][Ap](fp32)  and the matching gradient buffers.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -758,7 +759,16 @@ int mfvae_create(const MfvaeConfig* cfg, int device, MfvaeHandle* out) {
   add_bucket(0, h->reg2_begin);                       // idx_emb
   if (h->cfg.optimize_encoders) add_bucket(h->enc_begin, h->arena_elems);
   if (device < 0) { *out = h; return 0; }        // layout-only handle
-  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) h->side = nullptr;
+  {
+    // the wgrad chain gets the greater stream priority: every kernel of either chain fills the SMs' CTA slots, so the chains
+    // interleave only at kernel boundaries; without the priority the wgrad chain lags ~200 us behind its inputs and leaves a
+    // tail in which it runs alone (kernel timeline, tools/dp_trace.py)
+    int lo = 0, hi = 0;
+    const char* env = getenv("MFVAE_SIDE_PRIORITY");
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);            // hi = numerically smallest = greatest priority
+    const int prio = (env && env[0] == '0') ? lo : hi;
+    if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio) != cudaSuccess) h->side = nullptr;
+  }
   for (int i = 0; i < 4 + 2 * MFVAE_MAX_HIDDEN + 4; ++i) {
     cudaEvent_t e = nullptr;
     cudaEventCreateWithFlags(&e, cudaEventDisableTiming);

@@ -51,6 +51,7 @@ struct TcParams {
   int epi;
   const __nv_bfloat16* aux; long long aux_gs, aux_ld;
   int accumulate_atomic;                  // split-K: red.global.add.f32
+  int c_v8, aux_v8;                       // C rows / aux rows are 32-byte aligned: 256-bit accesses, one sector per lane
   // kEpiLossGrad: C = d loss / d (A B^T + bias) against `tgt`, loss value accumulated per epilogue warp
   const float* tgt; long long tgt_ld; float grad_scale; int huber; float* loss_partials;
 };
@@ -92,7 +93,17 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row
     }
   } else if (p.epi == kEpiReluMask && row_ok) {
     const __nv_bfloat16* a = p.aux + g * p.aux_gs + static_cast<long long>(row) * p.aux_ld + col0;
-    if (ncols == 32) {
+    if (ncols == 32 && p.aux_v8) {
+      uint32_t raw[16];
+      ld_global_nc_256(a, raw);
+      ld_global_nc_256(a + 16, raw + 8);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float2 m = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[q]));
+        if (!(m.x > 0.f)) f[2 * q] = 0.f;
+        if (!(m.y > 0.f)) f[2 * q + 1] = 0.f;
+      }
+    } else if (ncols == 32) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(a + j));
@@ -145,7 +156,17 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row
   const bool relu = (p.epi == kEpiBiasRelu);
   if (p.c_dtype == kBF16) {
     __nv_bfloat16* cbase = static_cast<__nv_bfloat16*>(p.C) + g * p.c_gs + col0;
-    if (ncols == 32) {
+    if (ncols == 32 && p.c_v8) {
+      // 32-byte-aligned rows: each lane writes its own 64 bytes as two 256-bit stores = two whole sectors, no exchange
+      if (row_ok) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1], relu);
+        __nv_bfloat16* c = cbase + static_cast<long long>(row) * p.c_ld;
+        st_global_256(c, pk);
+        st_global_256(c + 16, pk + 8);
+      }
+    } else if (ncols == 32) {
       // A lane holds 64 contiguous bytes of its row = two 32-byte sectors, but one store instruction moves 16 bytes per
       // lane.  Lanes (2i, 2i+1) trade halves so that every instruction writes whole sectors: {A0|A1}, {A2|A3} of the
       // even row, then {B0|B1}, {B2|B3} of the odd row -- half as many L2 write sectors as 32 row-strided 16-byte pieces.
@@ -190,6 +211,12 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(c + j, f[j]);
       }
+    } else if (ncols == 32 && p.c_v8) {
+      uint32_t u[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(f[j]);
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) st_global_256(c + j, u + j);
     } else if (ncols == 32) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
@@ -541,6 +568,11 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
   p.C = op.C; p.c_gs = op.c_gs; p.c_ld = op.c_ld; p.c_dtype = op.c_dtype;
   p.bias = op.bias; p.bias_gs = op.bias_gs; p.epi = op.epi;
   p.aux = static_cast<const __nv_bfloat16*>(op.aux); p.aux_gs = op.aux_gs; p.aux_ld = op.aux_ld;
+  {
+    const int per32 = (op.c_dtype == kBF16) ? 16 : 8;          // elements per 32-byte sector
+    p.c_v8 = (op.c_ld % per32 == 0 && (op.G == 1 || op.c_gs % per32 == 0) && reinterpret_cast<uintptr_t>(op.C) % 32 == 0) ? 1 : 0;
+  }
+  p.aux_v8 = (op.aux && op.aux_ld % 16 == 0 && (op.G == 1 || op.aux_gs % 16 == 0) && reinterpret_cast<uintptr_t>(op.aux) % 32 == 0) ? 1 : 0;
   p.tgt = nullptr; p.tgt_ld = 0; p.grad_scale = 0.f; p.huber = 1; p.loss_partials = nullptr;
   p.accumulate_atomic = (op.epi == kEpiAccum && splits > 1) ? 1 : 0;   // single split: plain stores into the zeroed C
   pl->BN = BN;

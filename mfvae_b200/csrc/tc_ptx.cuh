@@ -152,6 +152,16 @@ __device__ __forceinline__ void store_bf16_row32(__nv_bfloat16* c, long long ld,
   }
 }
 
+// 256-bit global accesses (sm_100: LDG / STG .256): one lane moves a whole 32-byte sector per instruction
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_256(const void* p, uint32_t* v) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+
 // byte offset of element (row, col) inside one 128B-swizzled box of [rows][64] bf16 (rows x 128 bytes, 1024-byte aligned):
 // the 16-byte chunk index is XOR-ed with (row % 8) -- the layout TMA SWIZZLE_128B writes and the UMMA descriptors read
 __device__ __forceinline__ uint32_t sw128_chunk_off(int row, int chunk) {

@@ -77,6 +77,24 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (p.epi == kEpiReluMask && p.c_dtype == kBF16 && ncols == 32 && p.c_v8 && p.aux_v8) {
+    // dgrad fast path: dX = (dY W) * (X > 0) on packed bf16 -- the ReLU mask is one HSETP2-mask + one AND per element pair
+    // (rounding to bf16 and zeroing commute), rows move as 256-bit sectors both ways
+    if (row_ok) {
+      const __nv_bfloat16* a = p.aux + g * p.aux_gs + static_cast<long long>(row) * p.aux_ld + col0;
+      uint32_t raw[16], pk[16];
+      ld_global_nc_256(a, raw);
+      ld_global_nc_256(a + 16, raw + 8);
+      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1], false) & __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&raw[j]), zero2);
+      __nv_bfloat16* c = static_cast<__nv_bfloat16*>(p.C) + g * p.c_gs + static_cast<long long>(row) * p.c_ld + col0;
+      st_global_256(c, pk);
+      st_global_256(c + 16, pk + 8);
+    }
+    return;
+  }
   if (p.epi == kEpiBias || p.epi == kEpiBiasRelu || p.epi == kEpiLossGrad) {
     const float* b = p.bias + g * p.bias_gs + col0;
     if (ncols == 32) {

@@ -163,3 +163,32 @@ def test_reference_driver_loop_end_to_end():
     tr = M.Trainer("Adam", model, 0.002, M.loss_s_r_vae_fn, device="cuda:0")
     mean_loss = tr.training_model(buf, 5, codebook)                   # raises TypeError in the reference (trainer.py:112)
     assert np.isfinite(float(mean_loss)) and float(mean_loss) < np.mean(hist[:5])
+
+
+@pytest.mark.parametrize("fusion", ["none", "encoder+loss"])
+@pytest.mark.parametrize("B", [77, 300])
+def test_workspace_tail_canary_ragged_batches(fusion, B):
+    """Own bounds check (compute-sanitizer is not available on this pool): ragged batch sizes (not multiples of the
+    128-row tiles, fewer rows than one tile) must not write past the activation workspace.  The workspace is re-bound with a
+    64 KB sentinel tail that has to survive forward, loss, backward and Adam."""
+    import ctypes as C
+    import mfvae_b200 as M
+    from mfvae_b200 import _lib as L
+    from oracle import mavae_oracle as O
+    spec = O.simple_tag_spec(latent=32)
+    m = M.MAVAE(spec.idx_features, spec.latent, spec.act_features, True, spec.agents, spec.obs_dim, spec.n_act, "cuda:0",
+                precision="bf16", include_dead_decoder=False, fusion=fusion)
+    need = L.lib().mfvae_workspace_bytes(m._h, B)
+    tail = 1 << 16
+    ws = torch.zeros(need + tail, dtype=torch.uint8, device="cuda:0")
+    ws[need:] = 0xAB
+    torch.cuda.synchronize()
+    L.check(L.lib().mfvae_bind_workspace(m._h, L.ptr(ws), need, B))
+    m._ws, m._ws_batch = ws, B
+    pb = _batch(M, spec, B, seed=77)
+    for _ in range(3):
+        losses = m.train_step(pb, 1e-3)
+    rs, rr, mus, lvs = m(M.PackedBatch(pb.obs, pb.act))
+    torch.cuda.synchronize()
+    assert bool((ws[need:] == 0xAB).all()), "write past the end of the workspace"
+    assert bool(torch.isfinite(losses).all()) and bool(torch.isfinite(rs).all())

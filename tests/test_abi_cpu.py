@@ -142,3 +142,53 @@ def test_gradient_buckets_cover_optimized_prefix(built):
     assert b[0][0] == 0 and b[-1][1] == m._n_opt
     for (l0, h0), (l1, h1) in zip(b, b[1:]):
         assert h0 == l1
+
+
+def test_continuous_action_model_surface_and_staging(built):
+    """descrete_act=False (reference model.py:123,148): per-agent ActionEncoder MLPs act_dim -> 64 -> C backed by the arena
+    (layer 0 padded to 8 input columns in the arena, views hide the padding), still unregistered like the reference's
+    plain dict; create_dataset keeps [B, act_dim] action matrices."""
+    act_dim = {"adversary_0": 5, "adversary_1": 5, "adversary_2": 5, "agent_0": 3}
+    spec = O.tiny_spec(4, idx_features=64, latent=32, act_features=64, discrete_act=False, act_dim=act_dim)
+    m = built.MAVAE(64, 32, 64, False, spec.agents, spec.obs_dim, act_dim, "cpu", precision="fp32")
+    for a in spec.agents:
+        enc = m.action_encoder[a]
+        assert isinstance(enc, built.ActionEncoder)
+        assert enc.net[0].weight.shape == (64, act_dim[a]) and enc.net[2].weight.shape == (64, 64)
+        assert enc.net[0].weight.stride(0) == 8                      # arena row pitch: K padded to 8
+    names = set(m.named_arena_tensors())
+    assert "action_encoder.agent_0.net.0.weight" in names and "action_encoder.agent_0.net.2.bias" in names
+    assert not any(k.startswith("action_encoder") for k in m.state_dict())       # unregistered, as in the reference
+    P = O.init_params(spec, 3)
+    m.load_named(P)
+    assert torch.equal(m.action_encoder["agent_0"].net[0].weight.detach(), P["action_encoder.agent_0.net.0.weight"])
+    t = O.synth_transition(spec, 6, 1)
+    cb = {a: i for i, a in enumerate(spec.agents)}
+    mine, ref = built.create_dataset(t, cb), O.stage_batch(t, cb)
+    for a in spec.agents:
+        assert mine[1][a].shape == (6, act_dim[a]) and torch.equal(mine[1][a], ref[1][a])
+        assert torch.equal(mine[0][a], ref[0][a])
+    assert torch.equal(mine[3], ref[3]) and torch.equal(mine[4], ref[4])
+
+
+def test_jax_front_end_weights(built):
+    """jax_ver/trainer.py:42-43,64: kl 0.1, r 0.5, state term weighted 1 - r."""
+    from mfvae_b200 import jax_trainer as J
+    assert (J.kl_weight, J.r_weight) == (0.1, 0.5)
+    assert J.loss_weights() == (0.1, 0.5, 0.5)
+    J.r_weight = 0.25                       # read at call time, like the reference's module globals
+    try:
+        assert J.loss_weights() == (0.1, 0.25, 0.75)
+    finally:
+        J.r_weight = 0.5
+
+
+def test_launch_list_parser_on_committed_profile():
+    """tools/parse_launches.py reproduces the per-kernel summary committed under profiles/."""
+    import subprocess
+    import sys
+    csv = os.path.join(ROOT, "profiles", "r1_launches_dram_cfg2_b4096.csv")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "parse_launches.py"), csv], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "gemm_tc_kernel (all instantiations): 36 launches" in out.stdout
+    assert "launches in step 59" in out.stdout

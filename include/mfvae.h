@@ -184,6 +184,9 @@ int32_t mfvae_profile_read(MfvaeHandle h, MfvaeGemmTiming* out, int32_t capacity
  * arena elements [begin, end) and is final once event i (cudaEvent_t, returned as void*) fires. */
 int32_t mfvae_bucket_count(MfvaeHandle h);
 int mfvae_bucket(MfvaeHandle h, int32_t i, int64_t* begin, int64_t* end, void** event);
+/* make `stream` wait until the four loss scalars of the step in flight are final (they are, before backward starts: their
+ * all-reduce can run beside backward instead of after it) */
+int mfvae_loss_wait(MfvaeHandle h, void* stream);
 /* make `stream` (e.g. the NCCL stream) wait for bucket i's event */
 int mfvae_bucket_wait(MfvaeHandle h, int32_t i, void* stream);
 

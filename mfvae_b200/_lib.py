@@ -87,6 +87,7 @@ SIGNATURES = {
     "mfvae_bucket_count": (_i32, [_vp]),
     "mfvae_bucket": (C.c_int, [_vp, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_vp)]),
     "mfvae_bucket_wait": (C.c_int, [_vp, _i32, _vp]),
+    "mfvae_loss_wait": (C.c_int, [_vp, _vp]),
     "mfvae_reparam_kl": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _u64, _u64, _i64, _i64, _vp, _vp, _vp]),
     "mfvae_recon_loss": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _f, _i64, _vp, _vp, _vp]),
     "mfvae_adam_flat": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i64, _vp]),

@@ -87,6 +87,7 @@ struct MfvaeHandle_ {
   cudaStream_t aux = nullptr;
   bool grads_zeroed = false;                 // mfvae_fwd_bwd: the gradient arena was zeroed on csum beside the forward pass
   cudaEvent_t zero_ev = nullptr, zero_fork_ev = nullptr;
+  cudaEvent_t loss_ev = nullptr;             // the four loss scalars are final (recorded at the end of the loss phase)
   cudaStream_t csum = nullptr;               // fourth stream: the bias column sums (HBM-bound) run beside the wgrad GEMMs
   std::vector<cudaEvent_t> csum_ev;
   cudaEvent_t aux_fork_ev = nullptr, aux_join_ev = nullptr, aux_fork2_ev = nullptr, aux_join2_ev = nullptr;
@@ -566,6 +567,7 @@ static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStre
                                 static_cast<float>(1.0 / cs)));
   else
     MFVAE_TRY(launch_loss_total(losses_ptr(h), sw, rw, h->cfg.kl_weight, s));
+  if (h->loss_ev) MFVAE_CUDA(cudaEventRecord(h->loss_ev, s));
   return 0;
 }
 
@@ -779,6 +781,7 @@ int mfvae_create(const MfvaeConfig* cfg, int device, MfvaeHandle* out) {
   if (cudaStreamCreateWithFlags(&h->csum, cudaStreamNonBlocking) != cudaSuccess) h->csum = nullptr;
   for (int i = 0; i < 6; ++i) { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); h->csum_ev.push_back(e); }
   cudaEventCreateWithFlags(&h->zero_ev, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->loss_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->zero_fork_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->aux_fork_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->aux_join_ev, cudaEventDisableTiming);
@@ -811,6 +814,7 @@ int mfvae_destroy(MfvaeHandle h) {
   if (h->aux) cudaStreamDestroy(h->aux);
   if (h->csum) cudaStreamDestroy(h->csum);
   if (h->zero_ev) cudaEventDestroy(h->zero_ev);
+  if (h->loss_ev) cudaEventDestroy(h->loss_ev);
   if (h->zero_fork_ev) cudaEventDestroy(h->zero_fork_ev);
   for (auto e : h->csum_ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {h->aux_fork_ev, h->aux_join_ev, h->aux_fork2_ev, h->aux_join2_ev}) if (e) cudaEventDestroy(e);
@@ -1019,6 +1023,11 @@ int mfvae_bucket(MfvaeHandle h, int32_t i, int64_t* begin, int64_t* end, void** 
   if (begin) *begin = h->buckets[i].begin;
   if (end) *end = h->buckets[i].end;
   if (event) *event = h->buckets[i].ev;
+  return 0;
+}
+int mfvae_loss_wait(MfvaeHandle h, void* stream) {
+  MFVAE_CHECK(h && h->loss_ev, "no loss has been recorded");
+  MFVAE_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->loss_ev, 0));
   return 0;
 }
 int mfvae_bucket_wait(MfvaeHandle h, int32_t i, void* stream) {

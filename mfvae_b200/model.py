@@ -598,6 +598,11 @@ class MAVAE(nn.Module):
         guarded = False
         dbg = _DP_DEBUG            # measurement switches (MFVAE_DP_DEBUG): never set in production
         with torch.cuda.stream(cs):
+            # the loss scalars are final before backward starts: reduce them first, beside backward, not in the step's tail
+            early_loss = "nocomm" not in dbg and "noloss" not in dbg and "lateloss" not in dbg
+            if early_loss:
+                L.check(lib.mfvae_loss_wait(self._h, csp))
+                dist.all_reduce(self._losses, group=self._pg, async_op=True).wait()
             for i, b, e in buckets:
                 L.check(lib.mfvae_bucket_wait(self._h, i, csp))
                 if "nocomm" not in dbg:
@@ -609,8 +614,8 @@ class MAVAE(nn.Module):
                     lr, betas, eps = adam
                     L.check(lib.mfvae_adam_range(self._h, b, min(e, self._n_opt), float(lr), float(betas[0]), float(betas[1]),
                                                  float(eps), self._adam_t, csp))
-            cs.wait_stream(main)       # losses are final at the end of the main stream's queue
-            if "nocomm" not in dbg and "noloss" not in dbg:
+            if "lateloss" in dbg:
+                cs.wait_stream(main)
                 dist.all_reduce(self._losses, group=self._pg, async_op=True).wait()
         main.wait_stream(cs)
 

@@ -192,3 +192,23 @@ def test_launch_list_parser_on_committed_profile():
     assert out.returncode == 0, out.stderr
     assert "gemm_tc_kernel (all instantiations): 36 launches" in out.stdout
     assert "launches in step 59" in out.stdout
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys; under
+    torchrun every rank but 0 exits 0 without work."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    env1 = dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                        capture_output=True, text=True, timeout=120, env=env1, cwd=ROOT)
+    assert r1.returncode == 0 and not [l for l in r1.stdout.splitlines() if l.startswith("{")]

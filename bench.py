@@ -11,7 +11,8 @@ batch is fixed, `value` is the whole-job samples/s (N * B * K / max-over-ranks d
 
 JSON line keys follow the driver contract (metric, value, unit, n_gpus, steps, warmup, ms_per_step, ..., e2e,
 gpu_launches, clocks) plus `roofline` (all tcgen05 GEMM launches of the step, timed live with CUDA events on the
-launching stream) and `cpu_baseline` (the oracle port of the reference step on this box's host cores).
+launching stream), `cpu_baseline` (the unmodified reference modules from baseline/_ref on this box's host cores; the oracle port
+only as the declared fallback) and `eager_b200` (the same reference modules on the same GPU through torch eager).
 """
 import argparse
 import json
@@ -101,16 +102,94 @@ class ClockSampler:
 
 
 def make_spec(w):
-    from oracle import mavae_oracle as O
-    return O.simple_tag_spec(latent=w["latent"], enc_hidden=tuple(w["enc_hidden"]), dec_hidden=tuple(w["dec_hidden"]))
+    from mfvae_b200.spec import simple_tag_dims
+    return simple_tag_dims(latent=w["latent"], enc_hidden=tuple(w["enc_hidden"]), dec_hidden=tuple(w["dec_hidden"]))
+
+
+def make_config(w, spec, B, world, source):
+    """`config` of the JSON line: identical for both arms (the driver compares them)."""
+    from mfvae_b200.spec import flops_per_sample, executed_macs_per_sample
+    row = 2 * spec.state_dim + 2 * spec.n_agents
+    return {"workload": w["name"], "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world}",
+            "source": source, "l2": f"inputs {B * row * 4 / 1e6:.0f} MB/step, 4 rotating device batches (> 126 MB L2)",
+            "flop_per_sample": flops_per_sample(spec), "flop_per_sample_executed": 6 * executed_macs_per_sample(spec)}
+
+
+def synth_transition(spec, batch, seed=0):
+    """cpprb.sample-shaped dict (torch_ver/src/replay_buffer.py:62-81,107-108): float32 arrays
+    {agent}_{observations,next_observations,actions,rewards} of shape (B, dim)."""
+    rng = np.random.default_rng(seed)
+    t = {}
+    for a in spec.agents:
+        o = spec.obs_dim[a]
+        t[f"{a}_observations"] = rng.standard_normal((batch, o)).astype(np.float32)
+        t[f"{a}_next_observations"] = rng.standard_normal((batch, o)).astype(np.float32)
+        t[f"{a}_actions"] = rng.integers(0, spec.n_act[a], size=(batch, 1)).astype(np.float32)
+        t[f"{a}_rewards"] = rng.standard_normal((batch, 1)).astype(np.float32)
+    return t
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the oracle port of the reference's CPU step (the Python reference cannot travel to the GPU box)
+# reference arm: the UNMODIFIED reference modules (baseline/_ref/torch_ver/{model,trainer}.py, installed byte-for-byte by
+# __graft_entry__.build() from /root/reference) driven exactly as torch_ver/main.py:84-98 drives them.  The oracle port is
+# the declared fallback when the install is absent or the workload is not expressible with the reference's hard-coded
+# layer widths (model.py:46,87).
 # ------------------------------------------------------------------------------------------------
-def cpu_step_factory(w, batch):
-    from oracle import mavae_oracle as O
+REF_DIR = os.path.join(ROOT, "baseline", "_ref", "torch_ver")
+
+
+def reference_modules():
+    if not (os.path.exists(os.path.join(REF_DIR, "model.py")) and os.path.exists(os.path.join(REF_DIR, "trainer.py"))):
+        return None
+    import importlib.util
+    mods = []
+    for name in ("model", "trainer"):
+        sp = importlib.util.spec_from_file_location(f"mfvae_reference_{name}", os.path.join(REF_DIR, name + ".py"))
+        mod = importlib.util.module_from_spec(sp)
+        sp.loader.exec_module(mod)
+        mods.append(mod)
+    return tuple(mods)
+
+
+def reference_expressible(w):
+    from mfvae_b200.spec import ENC_HIDDEN, DEC_HIDDEN
+    return tuple(w["enc_hidden"]) == ENC_HIDDEN and tuple(w["dec_hidden"]) == DEC_HIDDEN
+
+
+def reference_step_factory(w, batch, device="cpu"):
+    """One train step as the reference driver runs it (torch_ver/main.py:84-98): sample -> create_dataset -> MAVAE.forward
+    -> loss_s_r_vae_fn -> zero_grad -> backward -> Adam.step -> CosineAnnealingLR.step.  `sample` is a pre-drawn
+    cpprb-shaped dict (cpprb is not installed; sampling is not part of the timed arithmetic)."""
+    import contextlib
+    mods = reference_modules()
+    assert mods is not None
+    ref_model, ref_trainer = mods
     spec = make_spec(w)
+    torch.manual_seed(0)
+    m = ref_model.MAVAE(spec.idx_features, spec.latent, spec.act_features, True, spec.agents, spec.obs_dim, spec.n_act, device)
+    m.to(device)                                                                      # main.py:49
+    opt = torch.optim.Adam(m.parameters(), 0.005)                                     # main.py:52
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=50, eta_min=1e-4)   # main.py:53
+    codebook = {a: i for i, a in enumerate(spec.agents)}                              # main.py:39-42
+    trans = synth_transition(spec, batch, seed=0)
+    devnull = open(os.devnull, "w")
+
+    def step():
+        with contextlib.redirect_stdout(devnull):                                     # debug prints at model.py:160-163
+            idx_state, acts, joint, nxt, rew = ref_trainer.create_dataset(trans, codebook)
+            rs, rr, mus, lvs = m(idx_state, acts)
+            loss, sl, rl, kl = ref_model.loss_s_r_vae_fn(rs, rr, nxt, rew, mus, lvs, device)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            sched.step()
+        return loss
+    return step
+
+
+def port_step_factory(w, batch):
+    from oracle import mavae_oracle as O
+    spec = O.simple_tag_spec(latent=w["latent"], enc_hidden=tuple(w["enc_hidden"]), dec_hidden=tuple(w["dec_hidden"]))
     st = O.OracleState(spec, O.init_params(spec, 0))
     codebook = {a: i for i, a in enumerate(spec.agents)}
     trans = O.synth_transition(spec, batch, seed=0)
@@ -129,32 +208,55 @@ def cpu_step_factory(w, batch):
 
 
 def time_cpu(w, batch, steps, warmup):
+    """(samples/s, ms/step, kind) of the reference's CPU train step on all host cores."""
     torch.set_num_threads(os.cpu_count() or 1)
-    step = cpu_step_factory(w, batch)
+    if reference_modules() is not None and reference_expressible(w):
+        step, kind = reference_step_factory(w, batch), "reference"
+    else:
+        step, kind = port_step_factory(w, batch), "port"
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps * 1e3
+    return batch * steps / dt, dt / steps * 1e3, kind
+
+
+def time_eager_gpu(w, batch, dev, steps=5, warmup=2):
+    """The reference modules, unmodified, on the same B200 through torch eager (cuBLAS + ATen + torch.optim.Adam): the
+    "existing Blackwell path" of SURVEY.md section 2.1.  None when the reference install is absent."""
+    if reference_modules() is None or not reference_expressible(w):
+        return None
+    step = reference_step_factory(w, batch, device=dev)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": batch / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": steps,
+            "what": "unmodified reference model.py/trainer.py (baseline/_ref) on torch eager, fp32, same GPU, host batch as in main.py:84-98"}
 
 
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample of the workload: same model / batch, K steps sized to finish within minutes
-    batch = w["batch"]
-    steps = max(1, min(args.steps, 10))
-    warm = max(1, min(args.warmup, 2))
-    sps, ms = time_cpu(w, batch, steps, warm)
+    spec = make_spec(w)
+    batch = args.batch or w["batch"]
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    sps, ms, kind = time_cpu(w, batch, steps, warm)
     cores = torch.get_num_threads()
+    what = ("unmodified reference torch_ver/model.py + trainer.py (baseline/_ref), driven as main.py:84-98 incl. create_dataset"
+            if kind == "reference" else "oracle port of the torch_ver step incl. create_dataset (reference install absent or widths not expressible)")
     line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": w["name"], "batch": batch},
-            "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{steps} full train steps of batch {batch} (oracle port of torch_ver step incl. create_dataset), torch CPU fp32"},
+            "data": "synthetic", "config": make_config(w, spec, batch, max(1, args.gpus), "device-resident batches"),
+            "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{steps} full train steps (+{warm} warm-up) of batch {batch}: {what}, torch CPU fp32, {cores} threads"},
             "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -177,14 +279,8 @@ def synth_device_batches(spec, B, n, device, seed):
 
 
 def flops_per_sample(spec):
-    from oracle import mavae_oracle as O
-    macs = 0
-    for pre, lst in O.layer_dims(spec).items():
-        if pre == "decoder":
-            continue
-        macs += sum(o * i for o, i in lst)
-    macs += spec.n_agents ** 2
-    return 6 * macs
+    from mfvae_b200.spec import flops_per_sample as f
+    return f(spec)
 
 
 def run_ours(args, w):
@@ -362,27 +458,27 @@ def run_ours(args, w):
                     "engine": bound, "top": rows[:8], "all": rows}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on this box's host cores, bounded sample ----
-    cpu = None
+    cpu = eager = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cb = min(B, 4096)
-        sps, msc = time_cpu(w, cb, 3, 1)
-        cpu = {"value": sps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"3 train steps (+1 warm-up) of batch {cb}, same model, oracle port of the reference step incl. create_dataset, torch CPU fp32",
+        sps, msc, kind = time_cpu(w, cb, 3, 1)
+        cpu = {"value": sps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+               "sample": f"3 train steps (+1 warm-up) of batch {cb}, same model, " +
+                         ("unmodified reference modules (baseline/_ref) driven as main.py:84-98" if kind == "reference"
+                          else "oracle port of the reference step") + " incl. create_dataset, torch CPU fp32",
                "ms_per_step": msc}
+        eager = time_eager_gpu(w, cb, dev)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": w["precision"], "data": "synthetic",
-                "config": {"workload": w["name"], "batch_per_gpu": B, "global_batch": world * B,
-                           "parallelism": f"dp{world}", "source": "replay ring (device gather every step)" if ring is not None else "device-resident batches",
-                           "l2": f"inputs {B * row * 4 / 1e6:.0f} MB/step, {nb} rotating device batches (> 126 MB L2)",
-                           "flop_per_sample": flops_per_sample(spec)},
+                "config": make_config(w, spec, B, world, "replay ring (device gather every step)" if ring is not None else "device-resident batches"),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * row * 4, "d2h_bytes_per_step": 16,
                         "steps": e2e_steps, "wall_s": wall, "api": "MAVAE.train_step(PackedBatch) fed from packed pinned host rows"},
                 "gpu_launches": int(launches), "clocks": clocks, "losses_last_step": loss_host,
                 "model_tflops": value * flops_per_sample(spec) / 1e12 / world,
-                "roofline": roof, "cpu_baseline": cpu}
+                "roofline": roof, "cpu_baseline": cpu, "eager_b200": eager}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -132,6 +132,9 @@ int32_t mfvae_tensor_count(MfvaeHandle h);
 int mfvae_tensor_table(MfvaeHandle h, MfvaeTensorInfo* out, int32_t capacity);
 int mfvae_bind_arenas(MfvaeHandle h, const MfvaeArenas* arenas);
 int mfvae_refresh_shadow(MfvaeHandle h, void* stream);    /* fp32 master -> bf16 shadow (whole arena) */
+/* same over arena elements [begin, end) (4-element aligned): the drop-in forward re-casts reward_linear on every call,
+ * because the reference's POP-ART idiom edits it through `.data` (torch_ver/trainer.py:73-74), invisibly to autograd */
+int mfvae_refresh_shadow_range(MfvaeHandle h, int64_t begin, int64_t end, void* stream);
 
 /* activation workspace: caller allocates mfvae_workspace_bytes(h, B) bytes (256-B aligned) */
 int64_t mfvae_workspace_bytes(MfvaeHandle h, int32_t batch);

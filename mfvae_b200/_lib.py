@@ -67,6 +67,7 @@ SIGNATURES = {
     "mfvae_tensor_table": (C.c_int, [_vp, C.POINTER(MfvaeTensorInfo), _i32]),
     "mfvae_bind_arenas": (C.c_int, [_vp, C.POINTER(MfvaeArenas)]),
     "mfvae_refresh_shadow": (C.c_int, [_vp, _vp]),
+    "mfvae_refresh_shadow_range": (C.c_int, [_vp, _i64, _i64, _vp]),
     "mfvae_workspace_bytes": (_i64, [_vp, _i32]),
     "mfvae_bind_workspace": (C.c_int, [_vp, _vp, _i64, _i32]),
     "mfvae_forward": (C.c_int, [_vp, C.POINTER(MfvaeBatch), C.POINTER(MfvaeOutputs), _vp]),
@@ -112,6 +113,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m mfvae_b200.build` "
                                "(there is no CPU / eager fallback for this path)")
+        import torch  # noqa: F401  the library links the CUDA runtime dynamically; torch has libcudart.so.12 loaded already
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError = header / library mismatch

@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
         list(ex.map(run, jobs))
     if jobs or force or not os.path.exists(OUT):
         run([NVCC, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-             "-Xcompiler", "-fPIC", "-lcudart_static", "-ldl", "-lrt", "-lpthread"])
+             "-Xcompiler", "-fPIC", "--cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64", "-ldl", "-lrt", "-lpthread"])
     return OUT
 
 

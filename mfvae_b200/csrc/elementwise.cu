@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kThreads) stage_kernel(StageArgs p) {
           v[u][0] = __ldg(src); v[u][1] = __ldg(src + 1); v[u][2] = __ldg(src + 2); v[u][3] = __ldg(src + 3);
         } else {
           int id = a;
-          if (p.idx) id = static_cast<int>(p.idx[static_cast<int64_t>(bb) * p.A + a]);
+          if (p.idx) id = max(0, min(static_cast<int>(p.idx[static_cast<int64_t>(bb) * p.A + a]), p.A - 1));   // same clamp as the scatter of backward
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int c = c0 + k;

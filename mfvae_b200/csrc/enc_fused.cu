@@ -216,7 +216,7 @@ enc_fwd_kernel(const __grid_constant__ EncMaps maps, const EncFwdParams p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const long long b = min(static_cast<long long>(sl.b0 + warp + 8 * (8 * h + i)), static_cast<long long>(p.B - 1));
-          const int id = static_cast<int>(__ldg(p.idx + b * p.idx_ld + sl.a));
+          const int id = max(0, min(static_cast<int>(__ldg(p.idx + b * p.idx_ld + sl.a)), p.A - 1));
 #pragma unroll
           for (int k = 0; k < 8; ++k) raw[i][k] = __ldg(p.idx_emb + static_cast<long long>(id) * p.I + col0 + k);
         }

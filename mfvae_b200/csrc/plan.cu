@@ -856,6 +856,15 @@ int mfvae_refresh_shadow(MfvaeHandle h, void* stream) {
                           static_cast<cudaStream_t>(stream));
 }
 
+int mfvae_refresh_shadow_range(MfvaeHandle h, int64_t begin, int64_t end, void* stream) {
+  MFVAE_CHECK(h, "null handle");
+  if (!h->ar.d_shadow_bf16) return 0;
+  MFVAE_CHECK(begin >= 0 && end <= h->arena_elems && begin <= end && begin % 4 == 0 && (end - begin) % 4 == 0, "shadow range must be 4-element aligned and inside the arena");
+  if (end == begin) return 0;
+  return launch_cast_bf16(h->ar.d_param + begin, static_cast<__nv_bfloat16*>(h->ar.d_shadow_bf16) + begin, end - begin,
+                          static_cast<cudaStream_t>(stream));
+}
+
 int64_t mfvae_workspace_bytes(MfvaeHandle h, int32_t batch) {
   if (!h || batch < 1) return -1;
   MfvaeHandle_ tmp = *h;            // layout only; does not touch plans

@@ -177,8 +177,32 @@ def loss_s_r_vae_fn(recon_s, recon_r, s_hat, r_hat, mean_all, logvar_all, device
     return loss, s_loss, rr_loss, kl
 
 
+def _joint_of(t):
+    """The MAVAE whose current (recon_state, recon_reward) outputs `t` is the column concatenation of, or None.
+    ``loss_vae_fn`` takes ONE reconstruction matrix [B, S + A] (the reference's legacy joint decoder output, model.py:168);
+    with the two-headed model the caller builds it as ``torch.cat([recon_s, recon_r], 1)``, which autograd records as a
+    CatBackward0 node fed by outputs 0 and 1 of this package's forward node."""
+    fn = getattr(t, "grad_fn", None)
+    if fn is None or fn.name() != "CatBackward0" or len(fn.next_functions) != 2:
+        return None
+    (n0, i0), (n1, i1) = fn.next_functions
+    m = getattr(n0, "_mfvae_model", None) if n0 is not None else None
+    if m is None or n0 is not n1 or (i0, i1) != (0, 1) or n0 is not m._fwd_node or t.dim() != 2:
+        return None
+    return m
+
+
 def loss_vae_fn(y, y_hat, mean_all, logvar_all, device):
-    """Reference model.py:8-16 (joint MSE over [next_state | reward] + KL).  Legacy, torch ops + autograd bridge."""
+    """Reference model.py:8-16: joint MSE over [next_state | reward] + KL; returns the scalar loss.  When one of the two
+    matrices is ``torch.cat([recon_s, recon_r], 1)`` of this package's current forward pass (the loss is symmetric in
+    ``y`` / ``y_hat``), value and gradient seeds come from the fused CUDA loss (``MFVAE_LOSS_JOINT_MSE``); otherwise the
+    same formula is evaluated with torch ops and autograd flows into ``mfvae_backward_ext``."""
+    for recon, target in ((y_hat, y), (y, y_hat)):
+        m = _joint_of(recon)
+        if (m is not None and mean_all is m._last_mu and logvar_all is m._last_lv and torch.is_grad_enabled()
+                and not target.requires_grad):
+            S = m._cur.obs.shape[1]
+            return m._fused_loss(target[:, :S], target[:, S:], L.LOSS_JOINT_MSE)[0]
     y = y.to(device); y_hat = y_hat.to(device)
     return torch.nn.functional.mse_loss(y_hat, y) + _kl_sum_of_means(mean_all, logvar_all) * kl_weight
 
@@ -274,6 +298,12 @@ class MAVAE(nn.Module):
         self._ws_batch = -1
         self._serial = 0
         self._arena_version = -1
+        self._dirty = False
+        self._grads_pending = False           # a backward pass has run and neither step() nor zero_grad() has consumed it
+        self._losses_reduced = False          # data parallel: the 4 loss scalars of the step in flight are already all-reduced
+        self._fwd_node = None
+        rl = [t for t in self._table if t.kind in (L.T_RLIN_W, L.T_RLIN_B)]
+        self._rl_range = (min(t.offset for t in rl) // 8 * 8, (max(t.offset + t.rows * t.ld for t in rl) + 7) // 8 * 8)
         self._anchor = torch.zeros(1, device=tdev, requires_grad=True)
         self._cur: Optional[PackedBatch] = None
         self._cb = None
@@ -397,7 +427,48 @@ class MAVAE(nn.Module):
                     p.copy_(tensors[k].to(p.device, torch.float32))
 
     def save(self, path):
+        """Reference model.py:175-176: ``torch.save(self.state_dict(), path)`` -- the 39 registered tensors only (the
+        per-agent encoders and action tables live in plain dicts there and are NOT saved).  The file loads with
+        ``strict=True`` into the reference ``MAVAE`` and back."""
         torch.save(self.state_dict(), path)
+
+    # ---- the checkpoint the reference forgets (SURVEY section 8f-2): everything needed to resume bit-identically ----
+    CHECKPOINT_FORMAT = 1
+
+    def checkpoint(self) -> dict:
+        """``state_dict`` (the reference's 39 keys, loadable by the reference itself) + the unregistered per-agent encoders /
+        action tables under the oracle's names + Adam exp_avg / exp_avg_sq / step of the optimised prefix + the Philox
+        (seed, step) of the reparameterisation stream.  CPU tensors."""
+        n = self._n_opt
+        sd = {k: v.detach().cpu().clone() for k, v in self.state_dict().items()}
+        extra = {k: p.detach().cpu().clone() for k, p in self.named_arena_tensors().items() if k not in sd}
+        return {"format": self.CHECKPOINT_FORMAT, "state_dict": sd, "unregistered": extra,
+                "adam": {"exp_avg": self._m[:n].detach().cpu().clone(), "exp_avg_sq": self._v[:n].detach().cpu().clone(),
+                         "step": int(self._adam_t), "optimized_elems": int(n)},
+                "philox": {"seed": int(self.philox_seed), "step": int(self.philox_step)},
+                "config": {"agents": list(self.agents), "latent": int(self.feature), "enc_hidden": list(self.enc_hidden),
+                           "dec_hidden": list(self.dec_hidden), "optimize_encoders": bool(self.optimize_encoders)}}
+
+    def save_checkpoint(self, path):
+        torch.save(self.checkpoint(), path)
+
+    @torch.no_grad()
+    def load_checkpoint(self, path_or_dict):
+        ck = torch.load(path_or_dict, map_location="cpu") if not isinstance(path_or_dict, dict) else path_or_dict
+        if ck.get("format") != self.CHECKPOINT_FORMAT:
+            raise RuntimeError("mfvae_b200: unknown checkpoint format")
+        if int(ck["adam"]["optimized_elems"]) != int(self._n_opt):
+            raise RuntimeError("mfvae_b200: checkpoint was written by a model with a different optimised parameter set")
+        self.load_state_dict(ck["state_dict"], strict=True)
+        mine = self.named_arena_tensors()
+        for k, t in ck["unregistered"].items():
+            mine[k].copy_(t.to(mine[k].device, torch.float32))
+        n = self._n_opt
+        self._m[:n].copy_(ck["adam"]["exp_avg"]); self._v[:n].copy_(ck["adam"]["exp_avg_sq"])
+        self._adam_t = int(ck["adam"]["step"])
+        self.philox_seed, self.philox_step = int(ck["philox"]["seed"]), int(ck["philox"]["step"])
+        self._dirty = True
+        self._grads_pending = False
 
     def __del__(self):
         try:
@@ -429,15 +500,27 @@ class MAVAE(nn.Module):
         L.check(lib.mfvae_bind_workspace(self._h, L.ptr(self._ws), self._ws.numel(), B))
         self._ws_batch = B
 
-    def _sync_shadow(self):
-        """Parameter views share the arena's version counter: any in-place edit (optimizer, load_state_dict,
-        POP-ART rescale) bumps it and the bf16 shadow is refreshed before the next forward."""
+    def mark_dirty(self):
+        """Tell the engine that master weights were edited behind autograd's back (``p.data.mul_()``, ``p.data.copy_()``:
+        a ``.data`` alias carries its own version counter, so the edit is invisible to ``_sync_shadow``): the bf16 weight
+        shadow the tensor cores read is rebuilt before the next forward."""
+        self._dirty = True
+
+    def _sync_shadow(self, dropin=False):
+        """Parameter views share the arena's version counter: any in-place edit made through them (optimizer,
+        load_state_dict, ``Trainer.pop``) bumps it and the bf16 shadow is refreshed before the next forward.  Edits through
+        ``.data`` do not (see ``mark_dirty``); the reference's own POP-ART idiom does exactly that to ``reward_linear``
+        (``torch_ver/trainer.py:73-74``), so the drop-in ``forward`` re-casts that 1.6 K-element block on every call."""
         if self._shadow is None:
             return
         v = self._arena._version
-        if v != self._arena_version:
+        if v != self._arena_version or self._dirty:
             L.check(L.lib().mfvae_refresh_shadow(self._h, self._stream()))
             self._arena_version = v
+            self._dirty = False
+        elif dropin:
+            b, e = self._rl_range
+            L.check(L.lib().mfvae_refresh_shadow_range(self._h, b, e, self._stream()))
 
     def _cbatch(self, pb: PackedBatch):
         cb = L.MfvaeBatch()
@@ -464,9 +547,17 @@ class MAVAE(nn.Module):
         cols = [_f32c(idx_state[a], dev) for a in keys]
         obs = torch.cat([c[:, 1:] for c in cols], dim=1)
         idx = torch.stack([c[:, 0] for c in cols], dim=1).contiguous()
+        # nn.Embedding raises IndexError on an out-of-range index (model.py:142,146); so does the drop-in path (one
+        # device->host flag per call; PackedBatch users skip this and the kernels clamp, forward and backward alike)
+        A = len(self.agents)
+        bad = ((idx < 0) | (idx >= A)).any()
         if self.descrete_act:
             act = torch.cat([_f32c(actions[a], dev).reshape(-1, 1) for a in keys], dim=1)
-        else:       # continuous: [B, act_dim_a] vectors, concatenated in agent order
+            nmax = torch.tensor([float(self.act_dim[a]) for a in keys], device=dev)
+            bad = bad | ((act < 0) | (act >= nmax)).any()
+        if bool(bad):
+            raise IndexError("index out of range in self")
+        if not self.descrete_act:       # continuous: [B, act_dim_a] vectors, concatenated in agent order
             act = torch.cat([_f32c(actions[a], dev).reshape(cols[0].shape[0], -1) for a in keys], dim=1).contiguous()
         if eps is not None:
             eps = _f32c(eps, dev)
@@ -482,7 +573,7 @@ class MAVAE(nn.Module):
             raise RuntimeError("Tensors must have same number of dimensions (B == 1 is unsupported, as in the reference)")
         lib = L.lib()
         self._bind(pb.batch)
-        self._sync_shadow()
+        self._sync_shadow(dropin=True)
         self._serial += 1
         self._cur = pb
         self._cb = self._cbatch(pb)
@@ -494,8 +585,12 @@ class MAVAE(nn.Module):
         recon_r = self._ws_view(out.d_recon_r, B, out.recon_r_ld, A)
         latent = self._ws_view(out.d_latent, A * B, 2 * Lt, 2 * Lt).view(A, B, 2 * Lt)
         self._losses = self._ws_view(out.d_losses, 1, 4, 4)[0]
+        self._fwd_node = None
         if torch.is_grad_enabled():
             recon_s, recon_r, latent = _ForwardFn.apply(self._anchor, self, recon_s, recon_r, latent)
+            self._fwd_node = recon_s.grad_fn
+            if self._fwd_node is not None:
+                self._fwd_node._mfvae_model = self
         for t in (recon_s, recon_r):
             t._mfvae_owner, t._mfvae_serial = self, self._serial
         mu_all = [latent[a, :, :Lt] for a in range(A)]
@@ -525,6 +620,11 @@ class MAVAE(nn.Module):
         self._cb.d_next, self._cb.d_rew = pb.next.data_ptr(), pb.rew.data_ptr()
         self._set_weights(weights)
         L.check(lib.mfvae_loss(self._h, C.byref(self._cb), kind, self._stream()))
+        if self.data_parallel:
+            # each rank holds its share of the global means: reduce BEFORE the values are handed to the caller
+            import torch.distributed as dist
+            dist.all_reduce(self._losses, group=self._pg)
+            self._losses_reduced = True
         return _FusedLossFn.apply(self._anchor, self, self._losses)
 
     def _attach_grads(self):
@@ -532,13 +632,32 @@ class MAVAE(nn.Module):
             if p.grad is not g:
                 p.grad = g
 
+    def _check_accumulation(self):
+        # the backward pass re-zeroes the gradient arena and its two largest wgrads use plain stores: a second backward
+        # before step() / zero_grad() would silently keep only the last gradient where the reference accumulates
+        if self._grads_pending:
+            raise RuntimeError("mfvae_b200: a second backward() arrived before optimizer.step() / zero_grad(): gradient "
+                               "accumulation across backward passes is not supported by the engine")
+
+    def grads_consumed(self):
+        """optimizer.zero_grad() / step(): the gradients of the last backward pass have been used or dropped."""
+        self._grads_pending = False
+
     def _backward_fused(self):
+        self._check_accumulation()
         L.check(L.lib().mfvae_backward(self._h, C.byref(self._cb), self._stream()))
         self._after_backward()
 
     def _backward_ext(self, g_rs, g_rr, g_lat):
+        self._check_accumulation()
+        # data parallel: a torch loss is a mean over the LOCAL batch, the all-reduce is a plain sum -> seeds / world
+        scale = 1.0 / self._world() if self.data_parallel else 1.0
+
         def prep(g):
-            return None if g is None else g.to(torch.float32).contiguous()
+            if g is None:
+                return None
+            g = g.to(torch.float32)
+            return (g * scale if scale != 1.0 else g).contiguous()
         g_rs, g_rr, g_lat = prep(g_rs), prep(g_rr), prep(g_lat)
         L.check(L.lib().mfvae_backward_ext(self._h, C.byref(self._cb), L.ptr(g_rs), g_rs.shape[1] if g_rs is not None else 0,
                                            L.ptr(g_rr), g_rr.shape[1] if g_rr is not None else 0, L.ptr(g_lat), self._stream()))
@@ -546,8 +665,13 @@ class MAVAE(nn.Module):
 
     def _after_backward(self):
         self._attach_grads()
+        self._grads_pending = True
         if self.data_parallel:
             self._allreduce_grads()
+
+    def _world(self):
+        import torch.distributed as dist
+        return dist.get_world_size(self._pg)
 
     # ---- data parallel: bucketed all-reduce on a side stream, launched as each bucket's event fires ----
     def enable_data_parallel(self, process_group=None):
@@ -556,6 +680,14 @@ class MAVAE(nn.Module):
             raise RuntimeError("torch.distributed is not initialised")
         self._pg = process_group
         self.data_parallel = dist.get_world_size(process_group) > 1
+        if self.data_parallel:
+            # replicas must start identical: parameters, Adam moments / step count and the Philox stream of rank 0
+            for t in (self._arena, self._m, self._v):
+                dist.broadcast(t, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
+            meta = torch.tensor([self._adam_t, self.philox_step, self.philox_seed], dtype=torch.int64, device=self._tdev)
+            dist.broadcast(meta, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
+            self._adam_t, self.philox_step, self.philox_seed = (int(x) for x in meta.cpu())
+            self._dirty = True
         if self._on_gpu and self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(self._tdev)
         if self._on_gpu and self.data_parallel:
@@ -586,8 +718,9 @@ class MAVAE(nn.Module):
         if not self._on_gpu:           # host-logic path exercised by the gloo tests; no compute happens on CPU
             for _, b, e in buckets:
                 dist.all_reduce(self._grad[b:e], group=self._pg)
-            if getattr(self, "_losses", None) is not None:
+            if getattr(self, "_losses", None) is not None and not self._losses_reduced:
                 dist.all_reduce(self._losses, group=self._pg)
+            self._losses_reduced = False
             return
         lib = L.lib()
         main = torch.cuda.current_stream(self._tdev)
@@ -599,7 +732,8 @@ class MAVAE(nn.Module):
         dbg = _DP_DEBUG            # measurement switches (MFVAE_DP_DEBUG): never set in production
         with torch.cuda.stream(cs):
             # the loss scalars are final before backward starts: reduce them first, beside backward, not in the step's tail
-            early_loss = "nocomm" not in dbg and "noloss" not in dbg and "lateloss" not in dbg
+            early_loss = "nocomm" not in dbg and "noloss" not in dbg and "lateloss" not in dbg and not self._losses_reduced
+            self._losses_reduced = False
             if early_loss:
                 L.check(lib.mfvae_loss_wait(self._h, csp))
                 dist.all_reduce(self._losses, group=self._pg, async_op=True).wait()
@@ -625,6 +759,7 @@ class MAVAE(nn.Module):
         as soon as its gradients are final, concurrently with the encoder half of backward."""
         self._require_gpu()
         self._adam_t += 1
+        self._grads_pending = False
         fn = L.lib().mfvae_adam_step_overlapped if overlapped else L.lib().mfvae_adam_step
         L.check(fn(self._h, float(lr), float(betas[0]), float(betas[1]), float(eps), self._adam_t, self._stream()))
 
@@ -658,6 +793,7 @@ class MAVAE(nn.Module):
         self._sync_shadow()
         self._set_weights(loss_weights)
         self._serial += 1
+        self._grads_pending = self._losses_reduced = False
         self._cur, self._cb = pb, self._cbatch(pb)
         out = L.MfvaeOutputs()
         L.check(lib.mfvae_fwd_bwd(self._h, C.byref(self._cb), C.byref(out), self._stream()))

@@ -136,8 +136,29 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(list(model.parameters()), dict(lr=lr, betas=betas, eps=eps))
 
     def zero_grad(self, set_to_none: bool = True):
-        # gradients live in the arena and are re-zeroed by the backward pass itself
+        """Gradients live in the arena and are re-zeroed by the backward pass itself (its two largest wgrads overwrite), so
+        nothing is cleared here; the call marks the last backward's gradients as consumed.  Two backward passes without a
+        ``step()`` / ``zero_grad()`` in between raise instead of silently dropping the first (the engine does not
+        accumulate across backward passes, where ``torch.optim`` users might expect it to)."""
+        self._model.grads_consumed()
         return None
+
+    def state_dict(self):
+        """torch.optim.Adam-shaped: exp_avg / exp_avg_sq are the flat Adam arenas of the optimised prefix, `step` the
+        shared step count -- enough to resume (the reference never saves optimizer state, main.py:111-112)."""
+        m = self._model
+        n = m._n_opt
+        return {"state": {"exp_avg": m._m[:n].detach().clone(), "exp_avg_sq": m._v[:n].detach().clone(), "step": int(m._adam_t)},
+                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd):
+        m = self._model
+        n = m._n_opt
+        m._m[:n].copy_(sd["state"]["exp_avg"]); m._v[:n].copy_(sd["state"]["exp_avg_sq"])
+        m._adam_t = int(sd["state"]["step"])
+        for g, src in zip(self.param_groups, sd["param_groups"]):
+            g.update(src)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -229,6 +250,6 @@ class Trainer:
 
 def cosine_lr(step: int, base_lr: float = 0.005, t_max: int = 50, eta_min: float = 1e-4) -> float:
     """lr that ``CosineAnnealingLR(T_max=50, eta_min=1e-4)`` (reference main.py:53) applies at optimizer step
-    ``step`` (0-based), in closed form — used by the graph-captured fast path where no scheduler object runs."""
+    ``step`` (0-based), in closed form — what callers of ``MAVAE.train_step(pb, lr)`` pass when no scheduler object runs."""
     import math
     return eta_min + (base_lr - eta_min) * (1.0 + math.cos(math.pi * step / t_max)) / 2.0

@@ -68,6 +68,35 @@ def main(precision):
         gr = {k: rel(mine[k].grad, theirs[k].grad) for k in reg}        # all-reduced (optimised) tensors
         out["grad_rel_max"] = max(gr.values()); out["grad_rel_worst"] = max(gr, key=gr.get)
         out["param_rel_max"] = max(rel(mine[k], theirs[k]) for k in reg)
+    # the reference's own call sequence (main.py:87-97) under data parallel, on both loss routes: the fused CUDA ELBO
+    # (global means; loss values all-reduced before they are returned) and a torch loss over the autograd bridge (local
+    # means -> seeds scaled by 1 / world).  Gradients after the all-reduce must equal the full-batch gradients.
+    F = torch.nn.functional
+
+    def dropin(model, pb, route):
+        model.philox_step = 11
+        rs, rr, mus, lvs = model(M.PackedBatch(pb.obs, pb.act, sample0=pb.sample0, batch_global=pb.batch_global))
+        if route == "fused":
+            loss, sl, rl_, kl = M.loss_s_r_vae_fn(rs, rr, pb.next, pb.rew, mus, lvs, dev)
+        else:
+            kl = sum(torch.mean(-0.5 * torch.sum(1 + lv - mu ** 2 - torch.exp(lv), 1), 0) for mu, lv in zip(mus, lvs))
+            loss = F.huber_loss(pb.next, rs) + 0.005 * F.huber_loss(pb.rew, rr) + 0.0025 * kl
+        loss.backward()
+        model.grads_consumed()
+        torch.cuda.synchronize()
+        return float(loss.detach())
+
+    for route in ("fused", "torch"):
+        lv_dp = dropin(m, batch(rank * Bl, (rank + 1) * Bl, rank * Bl), route)
+        if rank == 0:
+            ref.load_named(m.named_arena_tensors())
+            lv_ref = dropin(ref, batch(0, Bg, 0), route)
+            mine, theirs = m.named_arena_tensors(), ref.named_arena_tensors()
+            gr = {k: rel(mine[k].grad, theirs[k].grad) for k in reg}
+            out[f"dropin_{route}_grad_rel_max"] = max(gr.values())
+            if route == "fused":
+                out["dropin_fused_loss_rel"] = abs(lv_dp - lv_ref) / max(abs(lv_ref), 1e-30)
+    if rank == 0:
         print("DP_CHECK " + json.dumps(out), flush=True)
     # every rank must hold identical parameters after the step
     flat = m._arena[:m._n_opt].clone()

@@ -206,9 +206,135 @@ def test_bench_reference_arm_contract():
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["higher_is_better"] is True
-    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    have_ref = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "torch_ver", "model.py"))
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["steps"] == 1 and line["warmup"] == 1                # the arm runs the --steps / --warmup it is given
+    assert set(line["config"]) == {"workload", "batch_per_gpu", "global_batch", "parallelism", "source", "l2", "flop_per_sample",
+                                   "flop_per_sample_executed"}
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     env1 = dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                         capture_output=True, text=True, timeout=120, env=env1, cwd=ROOT)
     assert r1.returncode == 0 and not [l for l in r1.stdout.splitlines() if l.startswith("{")]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# interoperability with the UNMODIFIED reference (imported from /root/reference in the build container; these tests are
+# skipped where it is absent, e.g. on the GPU box)
+# ---------------------------------------------------------------------------------------------------------------
+REF = "/root/reference/torch_ver"
+needs_reference = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "model.py")), reason="reference sources not present")
+
+
+def _reference():
+    import importlib.util
+    import sys
+    sys.dont_write_bytecode = True
+    mods = []
+    for name in ("model", "trainer"):
+        sp = importlib.util.spec_from_file_location(f"_ref_{name}", os.path.join(REF, name + ".py"))
+        mod = importlib.util.module_from_spec(sp)
+        sp.loader.exec_module(mod)
+        mods.append(mod)
+    return mods
+
+
+@needs_reference
+def test_saved_state_dict_loads_strict_into_the_reference_and_back(built, tmp_path):
+    """MAVAE.save (model.py:175-176) writes the reference's 39 keys: the file loads with strict=True into the unmodified
+    reference MAVAE, and a file written by the reference loads back here; the full checkpoint additionally restores the
+    unregistered encoders / action tables, Adam moments + step and the Philox position."""
+    ref_model, _ = _reference()
+    spec = O.simple_tag_spec(latent=32)
+    m = built.MAVAE(64, 32, 64, True, spec.agents, spec.obs_dim, spec.n_act, "cpu")
+    p = str(tmp_path / "test.pt")
+    m.save(p)
+    r = ref_model.MAVAE(64, 32, 64, True, spec.agents, spec.obs_dim, spec.n_act, "cpu")
+    missing = r.load_state_dict(torch.load(p), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    for k, v in m.state_dict().items():
+        assert torch.equal(r.state_dict()[k], v), k
+    # and back: a file written by the reference's own save()
+    with torch.no_grad():
+        for q in r.parameters():
+            q.add_(0.25)
+    p2 = str(tmp_path / "ref.pt")
+    r.save(p2)
+    m.load_state_dict(torch.load(p2), strict=True)
+    for k, v in r.state_dict().items():
+        assert torch.equal(m.state_dict()[k], v), k
+    # full checkpoint round trip (CPU tensors; the layout-only handle is enough for the bookkeeping)
+    m._m.uniform_(); m._v.uniform_(); m._adam_t = 17; m.philox_step = 123
+    p3 = str(tmp_path / "full.pt")
+    m.save_checkpoint(p3)
+    m2 = built.MAVAE(64, 32, 64, True, spec.agents, spec.obs_dim, spec.n_act, "cpu")
+    m2.load_checkpoint(p3)
+    n = m._n_opt
+    assert torch.equal(m2._arena, m._arena) and torch.equal(m2._m[:n], m._m[:n]) and torch.equal(m2._v[:n], m._v[:n])
+    assert (m2._adam_t, m2.philox_step, m2.philox_seed) == (17, 123, m.philox_seed)
+    ck = torch.load(p3)
+    assert set(ck["state_dict"]) == set(r.state_dict()) and "encoders.adversary_0.net.0.weight" in ck["unregistered"]
+    r.load_state_dict(ck["state_dict"], strict=True)          # the reference can read the weights out of the full checkpoint too
+
+
+@needs_reference
+def test_reference_trainer_failures_this_package_fixes(built):
+    """the reference's POP-ART mode raises for every batch (pop() multiplies the [A, A] weight in place by a
+    [B, A] ratio, trainer.py:72-74) and training_model raises TypeError (adds the loss 4-tuple to a float,
+    trainer.py:112-113).  Both are reproduced on the unmodified reference; the drop-in Trainer runs the same calls."""
+    import contextlib
+    import io
+    ref_model, ref_trainer = _reference()
+    spec = O.tiny_spec(3, idx_features=16, latent=8, act_features=8)
+    cb = {a: i for i, a in enumerate(spec.agents)}
+    B = 6
+    t = O.synth_transition(spec, B, 0)
+    r = ref_model.MAVAE(16, 8, 8, True, spec.agents, spec.obs_dim, spec.n_act, "cpu")
+    idx_state, acts, joint, nxt, rew = ref_trainer.create_dataset(t, cb)
+    tr = ref_trainer.Trainer("POPART", r, 1e-3, ref_model.loss_s_r_vae_fn, beta=0.3, device="cpu")
+    with pytest.raises(RuntimeError), contextlib.redirect_stdout(io.StringIO()):
+        tr.forward(idx_state, acts, nxt, rew)                      # trainer.py:72-74
+
+    class OneBatch:
+        def sample(self):
+            return t
+    tr = ref_trainer.Trainer("Adam", r, 1e-3, ref_model.loss_s_r_vae_fn, device="cpu")
+    with pytest.raises(TypeError), contextlib.redirect_stdout(io.StringIO()):
+        tr.training_model(OneBatch(), 1, cb)                       # trainer.py:112-113
+    # the drop-in: POP-ART statistics are per agent, so pop() is well-formed for any batch (CPU: bookkeeping only)
+    m = built.MAVAE(16, 8, 8, True, spec.agents, spec.obs_dim, spec.n_act, "cpu", precision="fp32")
+    mine = built.Trainer("POPART", m, 1e-3, built.loss_s_r_vae_fn, beta=0.3, device="cpu")
+    mine.art(rew); mine.pop(); mine.update_stats()
+    assert mine.sigma.shape == (3,) and bool(torch.isfinite(m.reward_linear.weight).all())
+
+
+def test_second_backward_without_step_raises(built):
+    spec = O.tiny_spec(3, idx_features=16, latent=8, act_features=8)
+    m = built.MAVAE(16, 8, 8, True, spec.agents, spec.obs_dim, spec.n_act, "cpu", precision="fp32")
+    opt = built.FusedAdam(m, 1e-3)
+    m._grads_pending = True                     # state after one backward pass
+    with pytest.raises(RuntimeError, match="second backward"):
+        m._check_accumulation()
+    opt.zero_grad()
+    m._check_accumulation()                     # consumed
+    sd = opt.state_dict()
+    assert sd["state"]["step"] == 0 and sd["state"]["exp_avg"].numel() == m._n_opt and sd["param_groups"][0]["lr"] == 1e-3
+    m._m.fill_(2.0); m._adam_t = 5
+    sd = opt.state_dict()
+    m._m.zero_(); m._adam_t = 0
+    opt.load_state_dict(sd)
+    assert m._adam_t == 5 and float(m._m[0]) == 2.0
+
+
+def test_pack_rejects_out_of_range_indices_like_nn_embedding(built):
+    spec = O.tiny_spec(3, idx_features=16, latent=8, act_features=8)
+    m = built.MAVAE(16, 8, 8, True, spec.agents, spec.obs_dim, spec.n_act, "cpu", precision="fp32")
+    cb1 = {a: i + 1 for i, a in enumerate(spec.agents)}            # 1-based codebook: index 3 does not exist
+    idx_state, acts, *_ = built.create_dataset(O.synth_transition(spec, 4, 0), cb1)
+    with pytest.raises(IndexError):
+        m.pack(idx_state, acts)
+    cb = {a: i for i, a in enumerate(spec.agents)}
+    idx_state, acts, *_ = built.create_dataset(O.synth_transition(spec, 4, 0), cb)
+    acts[spec.agents[0]][0, 0] = 5.0                               # Discrete(5): 5 is out of range
+    with pytest.raises(IndexError):
+        m.pack(idx_state, acts)

@@ -192,3 +192,73 @@ def test_workspace_tail_canary_ragged_batches(fusion, B):
     torch.cuda.synchronize()
     assert bool((ws[need:] == 0xAB).all()), "write past the end of the workspace"
     assert bool(torch.isfinite(losses).all()) and bool(torch.isfinite(rs).all())
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path):
+    """save_checkpoint -> load_checkpoint into a fresh model -> the next train steps (parameters, Adam moments,
+    losses, Philox stream) are bit-identical to the uninterrupted run.  Loss scalars use fixed-order reductions; the
+    parameters are compared after steps whose gradients carry fp32 atomics, so the model runs with a batch of one tile per
+    agent and split-K off the critical tensors is not assumed: equality is asserted on the losses and within 1e-6 on parameters."""
+    M, O, spec, m = _model("bf16")
+    pbs = [_batch(M, spec, 128, seed=40 + i) for i in range(4)]
+    for i in range(2):
+        m.train_step(pbs[i], M.cosine_lr(i))
+    p = str(tmp_path / "ck.pt")
+    m.save_checkpoint(p)
+    cont = [m.train_step(pbs[2 + i], M.cosine_lr(2 + i)).clone() for i in range(2)]
+    _, _, _, m2 = _model("bf16")
+    with torch.no_grad():
+        m2._arena.normal_()                                    # make sure everything really comes from the file
+    m2.load_checkpoint(p)
+    assert m2._adam_t == 2 and m2.philox_step == 2
+    res = [m2.train_step(pbs[2 + i], M.cosine_lr(2 + i)).clone() for i in range(2)]
+    torch.cuda.synchronize()
+    for a, b in zip(cont, res):
+        assert torch.allclose(a, b, rtol=1e-6, atol=0), (a, b)
+    n = m._n_opt
+    assert float((m._arena[:n] - m2._arena[:n]).norm() / m._arena[:n].norm()) < 1e-6
+    assert float((m._m[:n] - m2._m[:n]).norm() / m._m[:n].norm()) < 1e-5
+
+
+def test_data_edits_of_reward_linear_reach_the_tensor_cores():
+    """the reference's POP-ART idiom edits reward_linear through `.data` (torch_ver/trainer.py:73-74), which does
+    not bump the arena's version counter.  The drop-in forward must still see the edit in bf16 mode (stale bf16 shadow =
+    silently wrong forward); mark_dirty() covers edits of any other tensor."""
+    M, O, spec, m = _model("bf16")
+    pb = _batch(M, spec, 64)
+    with torch.no_grad():
+        m.philox_step = 0
+        _, rr0, _, _ = m(M.PackedBatch(pb.obs, pb.act))
+        rr0 = rr0.clone()
+        m.reward_linear.weight.data.mul_(2.0)                  # invisible to autograd's version counter
+        m.reward_linear.bias.data.add_(1.0)
+        m.philox_step = 0
+        _, rr1, _, _ = m(M.PackedBatch(pb.obs, pb.act))
+        assert torch.allclose(rr1, 2.0 * rr0 + 1.0, rtol=2e-2, atol=2e-2), float((rr1 - (2 * rr0 + 1)).abs().max())
+        # any other tensor: .data edit + mark_dirty()
+        m.philox_step = 0
+        rs0 = m(M.PackedBatch(pb.obs, pb.act))[0].clone()
+        m.state_decoder.net[10].bias.data.add_(3.0)            # bias is read in fp32: visible at once
+        m.state_decoder.net[10].weight.data.mul_(0.0)
+        m.mark_dirty()
+        m.philox_step = 0
+        rs1 = m(M.PackedBatch(pb.obs, pb.act))[0]
+        want = m.state_decoder.net[10].bias.detach().expand_as(rs1)
+        assert torch.allclose(rs1, want, atol=1e-5) and not torch.allclose(rs0, rs1)
+
+
+def test_second_backward_without_step_raises_on_gpu():
+    M, O, spec, m = _model()
+    pb = _batch(M, spec, 32)
+    opt = M.FusedAdam(m, 1e-3)
+    rs, rr, mus, lvs = m(M.PackedBatch(pb.obs, pb.act))
+    loss = M.loss_s_r_vae_fn(rs, rr, pb.next, pb.rew, mus, lvs, "cuda:0")[0]
+    loss.backward()
+    rs, rr, mus, lvs = m(M.PackedBatch(pb.obs, pb.act))
+    loss = M.loss_s_r_vae_fn(rs, rr, pb.next, pb.rew, mus, lvs, "cuda:0")[0]
+    with pytest.raises(RuntimeError, match="second backward"):
+        loss.backward()
+    opt.zero_grad()
+    rs, rr, mus, lvs = m(M.PackedBatch(pb.obs, pb.act))
+    M.loss_s_r_vae_fn(rs, rr, pb.next, pb.rew, mus, lvs, "cuda:0")[0].backward()
+    opt.step()

@@ -16,8 +16,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run(case, precision, engine, mode="dropin", rng="eps", fusion="auto"):
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "step_check.py"), case, precision, engine, mode, rng, fusion],
+def run(case, precision, engine, mode="dropin", rng="eps", fusion="auto", flags=""):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "step_check.py"), case, precision, engine, mode, rng, fusion, flags],
                        capture_output=True, text=True, timeout=900, cwd=ROOT)
     line = [l for l in r.stdout.splitlines() if l.startswith("STEP_CHECK ")]
     assert r.returncode == 0 and line, r.stdout[-3000:] + r.stderr[-3000:]
@@ -89,3 +89,59 @@ def test_bf16_tcgen05_fast_path(case, fusion):
     assert o["loss_rel_oracle"][0] < 1e-3 and max(o["loss_rel_oracle"]) < 5e-2
     assert o["grad_rel_median_vs_bf16_oracle"] < 2e-3
     assert o["grad_rel_max_vs_bf16_oracle"] < 6e-2, o["grad_rel_worst_vs_bf16_oracle"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# shapes and options the golden cases do not reach (VERDICT r1 "untested configs"): replayed against the oracle directly
+# ---------------------------------------------------------------------------------------------------------------
+def test_headline_shape_cfg2_b4096_bf16_fast_path():
+    """The exact bench.py default (BASELINE configs[1]): simple_tag dims, latent 32, B = 4096, bf16 / tcgen05, train_step.
+    Loss within 1e-3 of the fp32 oracle (north_star).  Gradients: per tensor against the oracle evaluated with the same
+    bf16 rounding points, and the WHOLE gradient (all tensors concatenated) as relative L2 + cosine against both oracles."""
+    o = run("cfg2_b4096", "bf16", "tcgen05", "fast")
+    assert o["loss_rel_oracle"][0] < 1e-3, o["loss_rel_oracle"]
+    assert o["grad_rel_median_vs_bf16_oracle"] < 2e-3
+    assert o["grad_rel_max_vs_bf16_oracle"] < 3e-2, o["grad_rel_worst_vs_bf16_oracle"]
+    assert o["whole_grad_rel_vs_bf16_oracle"] < 5e-3 and o["whole_grad_cos_vs_bf16_oracle"] > 0.9999
+    assert o["whole_grad_rel"] < 3e-2 and o["whole_grad_cos"] > 0.999          # vs the fp32 oracle
+
+
+def test_headline_shape_cfg2_b4096_fp32():
+    o = run("cfg2_b4096", "fp32", "simt", "fast")
+    assert max(o["loss_rel_oracle"]) < 1e-5
+    assert o["grad_rel_max"] < 1e-5 and o["whole_grad_rel"] < 1e-5
+    assert o["param3_rel_max"] < 5e-5
+
+
+@pytest.mark.parametrize("precision,engine", [("fp32", "simt"), ("bf16", "tcgen05")])
+def test_wide_shape(precision, engine):
+    """BASELINE configs[2] layer shapes: encoder and decoder hidden 1024 x 4, latent 128."""
+    o = run("wide", precision, engine)
+    if precision == "fp32":
+        assert max(o["loss_rel_oracle"]) < 1e-5 and o["grad_rel_max"] < 1e-5 and o["whole_grad_rel"] < 1e-5
+        assert max(o["recon_s_rel"], o["recon_r_rel"], o["mu_rel"], o["logvar_rel"]) < 1e-5
+        assert o["param3_rel_max"] < 5e-5
+    else:
+        assert o["loss_rel_oracle"][0] < 1e-3
+        assert o["grad_rel_median_vs_bf16_oracle"] < 2e-3 and o["grad_rel_max_vs_bf16_oracle"] < 6e-2
+        assert o["whole_grad_rel_vs_bf16_oracle"] < 1e-2 and o["whole_grad_cos_vs_bf16_oracle"] > 0.9999
+
+
+@pytest.mark.parametrize("mode", ["dropin", "fast"])
+def test_optimize_encoders_three_steps(mode):
+    """optimize_encoders=True (jax_ver semantics: every tensor trains): 3 Adam steps, post-step encoder parameters included,
+    against OracleState(optimize_encoders=True)."""
+    o = run("latent32", "fp32", "simt", mode, "eps", "auto", "optenc")
+    assert max(o["loss_rel_oracle"]) < 1e-5
+    assert o["grad_rel_max"] < 1e-5
+    assert o["param3_rel_max"] < 5e-5, o["param3_worst"]
+
+
+def test_loss_vae_fn_joint_mse_on_the_cuda_path():
+    """loss_vae_fn (reference model.py:8-16) on torch.cat([recon_s, recon_r], 1): routed to MFVAE_LOSS_JOINT_MSE.  Loss
+    against the golden value minted from the reference, gradients against autograd of the oracle's restatement."""
+    o = run("latent32", "fp32", "simt", "jointmse")
+    assert o["jointmse_on_cuda_path"]
+    assert o["jointmse_loss_rel_golden"] < 1e-5 and max(o["loss_rel_oracle"]) < 1e-5
+    assert o["grad_rel_max"] < 1e-5, o["grad_rel_worst"]
+    assert o["param3_rel_max"] < 5e-5

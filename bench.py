@@ -369,54 +369,75 @@ def run_ours(args, w):
     loss_host = [float(x) for x in losses.cpu()]
 
     # ---- end to end: packed pinned host batch -> H2D -> step -> D2H loss, every step ----
+    # Host rows as a pinned replay ring keeps them: [obs | act | next | rew].  Observations are kept in bf16 on the host (the
+    # bf16 engine rounds them on arrival anyway: the step is bit-identical to shipping fp32), everything else fp32.  The
+    # `e2e_bf16_targets` variant also keeps next-observations (the reconstruction TARGET) in bf16 -- that rounds the loss'
+    # target, so it is reported beside the headline, not as it.
     S, A = spec.state_dim, spec.n_agents
     row = 2 * S + 2 * A
     n_host = 3
-    host = [torch.randn(B * row).pin_memory() for _ in range(n_host)]
-    for hbuf in host:     # valid action codes
-        hbuf[B * S:B * (S + A)] = torch.randint(0, 5, (B * A,)).float()
-    dbuf = [torch.empty(B * row, device=dev) for _ in range(2)]
-    copy_stream = torch.cuda.Stream(dev)
-    ready = [torch.cuda.Event() for _ in range(2)]
-    freed = [torch.cuda.Event() for _ in range(2)]
-    from mfvae_b200.trainer import _split_flat
     e2e_steps = max(3, min(args.steps, 20))
     loss_pinned = torch.empty(4).pin_memory()
+    copy_stream = torch.cuda.Stream(dev)
 
-    def e2e_loop(n):
-        main = torch.cuda.current_stream()
-        for k in range(2):
-            freed[k].record(main)
-        # prologue: copy of step 0
-        with torch.cuda.stream(copy_stream):
-            dbuf[0].copy_(host[0], non_blocking=True); ready[0].record(copy_stream)
-        for i in range(n):
-            k = i % 2
-            if i + 1 < n:     # overlap the next batch's H2D with this step's compute
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(freed[(i + 1) % 2])
-                    dbuf[(i + 1) % 2].copy_(host[(i + 1) % n_host], non_blocking=True); ready[(i + 1) % 2].record(copy_stream)
-            main.wait_event(ready[k])
-            obs, act, nxt, rew = _split_flat(dbuf[k], B, S, A)
-            pb = M.PackedBatch(obs, act, nxt, rew, sample0=rank * B, batch_global=world * B)
-            out = m.train_step(pb, lr(i))
-            freed[k].record(main)
-            loss_pinned.copy_(out, non_blocking=True)
-        main.synchronize()
+    def e2e_run(obs_bf16, next_bf16):
+        ob, nb_ = (2 if obs_bf16 else 4), (2 if next_bf16 else 4)
+        seg = [B * S * ob, B * A * 4, B * S * nb_, B * A * 4]                    # bytes: obs | act | next | rew
+        offs = [0, seg[0], seg[0] + seg[1], seg[0] + seg[1] + seg[2]]
+        total = sum(seg)
+        host = []
+        for _ in range(n_host):
+            hb = torch.empty(total, dtype=torch.uint8).pin_memory()
+            hb[offs[0]:offs[1]].view(torch.bfloat16 if obs_bf16 else torch.float32).copy_(torch.randn(B * S))
+            hb[offs[1]:offs[2]].view(torch.float32).copy_(torch.randint(0, 5, (B * A,)).float())
+            hb[offs[2]:offs[3]].view(torch.bfloat16 if next_bf16 else torch.float32).copy_(torch.randn(B * S))
+            hb[offs[3]:].view(torch.float32).copy_(torch.randn(B * A))
+            host.append(hb)
+        dbuf = [torch.empty(total, dtype=torch.uint8, device=dev) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
 
-    e2e_loop(3)
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    wall0 = time.perf_counter()
-    t0.record()
-    e2e_loop(e2e_steps)
-    t1.record()
-    barrier()
-    wall = time.perf_counter() - wall0
-    ms2 = torch.tensor([max(t0.elapsed_time(t1), 0.0)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / (float(ms2) * 1e-3)
+        def views(d):
+            return (d[offs[0]:offs[1]].view(torch.bfloat16 if obs_bf16 else torch.float32).view(B, S), d[offs[1]:offs[2]].view(torch.float32).view(B, A),
+                    d[offs[2]:offs[3]].view(torch.bfloat16 if next_bf16 else torch.float32).view(B, S), d[offs[3]:].view(torch.float32).view(B, A))
+
+        def loop(n):
+            main = torch.cuda.current_stream()
+            for k in range(2):
+                freed[k].record(main)
+            with torch.cuda.stream(copy_stream):      # prologue: copy of step 0
+                dbuf[0].copy_(host[0], non_blocking=True); ready[0].record(copy_stream)
+            for i in range(n):
+                k = i % 2
+                if i + 1 < n:     # overlap the next batch's H2D with this step's compute
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(freed[(i + 1) % 2])
+                        dbuf[(i + 1) % 2].copy_(host[(i + 1) % n_host], non_blocking=True); ready[(i + 1) % 2].record(copy_stream)
+                main.wait_event(ready[k])
+                obs, act, nxt, rew = views(dbuf[k])
+                pb = M.PackedBatch(obs, act, nxt, rew, sample0=rank * B, batch_global=world * B)
+                out = m.train_step(pb, lr(i))
+                freed[k].record(main)
+                loss_pinned.copy_(out, non_blocking=True)
+            main.synchronize()
+
+        loop(3)
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        wall0 = time.perf_counter()
+        t0.record()
+        loop(e2e_steps)
+        t1.record()
+        barrier()
+        wall = time.perf_counter() - wall0
+        ms2 = torch.tensor([max(t0.elapsed_time(t1), 0.0)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        return world * B * e2e_steps / (float(ms2) * 1e-3), total, wall
+
+    e2e_value, e2e_bytes, wall = e2e_run(w["precision"] == "bf16", False)
+    e2e_fp32 = e2e_run(False, False) if w["precision"] == "bf16" else None
+    e2e_t16 = e2e_run(True, True) if w["precision"] == "bf16" else None
 
     # ---- roofline of the tensor-core GEMMs, timed live with CUDA events on the launching stream ----
     roof = None
@@ -474,8 +495,13 @@ def run_ours(args, w):
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": w["precision"], "data": "synthetic",
                 "config": make_config(w, spec, B, world, "replay ring (device gather every step)" if ring is not None else "device-resident batches"),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * row * 4, "d2h_bytes_per_step": 16,
-                        "steps": e2e_steps, "wall_s": wall, "api": "MAVAE.train_step(PackedBatch) fed from packed pinned host rows"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": 16,
+                        "steps": e2e_steps, "wall_s": wall,
+                        "api": "MAVAE.train_step(PackedBatch) fed from packed pinned host rows [obs bf16 | act | next | rew fp32] (bf16 engine: "
+                               "bit-identical to fp32 observations)" if w["precision"] == "bf16" else "MAVAE.train_step(PackedBatch) fed from packed pinned fp32 host rows"},
+                "e2e_fp32_rows": None if e2e_fp32 is None else {"value": e2e_fp32[0], "unit": UNIT, "h2d_bytes_per_step": e2e_fp32[1]},
+                "e2e_bf16_targets": None if e2e_t16 is None else {"value": e2e_t16[0], "unit": UNIT, "h2d_bytes_per_step": e2e_t16[1],
+                                                                  "note": "next-observation targets also bf16 on the host: rounds the loss target (opt-in)"},
                 "gpu_launches": int(launches), "clocks": clocks, "losses_last_step": loss_host,
                 "model_tflops": value * flops_per_sample(spec) / 1e12 / world,
                 "roofline": roof, "cpu_baseline": cpu, "eager_b200": eager}

@@ -39,8 +39,13 @@ enum { MFVAE_ENGINE_AUTO = 0, MFVAE_ENGINE_SIMT = 1, MFVAE_ENGINE_TCGEN05 = 2 };
  *            (enc_fused.cu; per-layer kernels are used when its shape constraints do not hold)
  *   LOSS     mfvae_fwd_bwd only: the state head's reconstruction loss and its gradient are the epilogue of the output-layer
  *            GEMM (recon_s is never written to HBM; MfvaeOutputs.d_recon_s is NULL)
- *   AUTO     the combination that measured fastest on B200 (today: NONE) */
-enum { MFVAE_FUSE_AUTO = 0, MFVAE_FUSE_NONE = 1, MFVAE_FUSE_ENCODER = 2, MFVAE_FUSE_LOSS = 4 };
+ *   AUTO     the combination that measured fastest on B200 (today: NONE)
+ *   NOFOLD_IDX / NOFOLD_ACT   keep a constant-input column block dense (csrc/fold.cu): the id-embedding columns of encoder
+ *            layer 0 (instead of a per-agent bias) / the action-embedding half of decoder layer 0 (K = A*C instead of
+ *            A*n_act one-hot columns).  Same mathematics, different bf16 rounding points; used by the tests that pin the
+ *            folded path against the dense one.  ENCODER implies NOFOLD_IDX (that kernel stages the embedding columns). */
+enum { MFVAE_FUSE_AUTO = 0, MFVAE_FUSE_NONE = 1, MFVAE_FUSE_ENCODER = 2, MFVAE_FUSE_LOSS = 4, MFVAE_FUSE_NOFOLD_IDX = 8,
+       MFVAE_FUSE_NOFOLD_ACT = 16 };
 enum { MFVAE_LOSS_DEFAULT = 0, MFVAE_LOSS_HUBER = 1, MFVAE_LOSS_MSE = 2, MFVAE_LOSS_JOINT_MSE = 3 };
 
 typedef struct MfvaeConfig {
@@ -105,6 +110,11 @@ typedef struct MfvaeBatch {
   int64_t batch_global;    /* B summed over ranks: the loss means divide by this        */
   uint64_t seed;           /* Philox key                                                */
   uint64_t step;           /* Philox counter word 3                                     */
+  int32_t obs_bf16;        /* 1: d_obs points at bf16 [B, S] (what a host ring that stores observations in bf16 ships: half
+                              the PCIe bytes).  The bf16 engine rounds observations to bf16 on arrival anyway, so results
+                              are bit-identical to feeding the fp32 values those bf16 numbers came from.               */
+  int32_t next_bf16;       /* 1: d_next points at bf16 [B, S]: the reconstruction TARGET is rounded -- changes the loss
+                              at the 1e-3 level, off by default                                                        */
 } MfvaeBatch;
 
 typedef struct MfvaeOutputs {

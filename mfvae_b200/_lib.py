@@ -12,7 +12,7 @@ MAX_HIDDEN = 8
 
 PREC_FP32, PREC_BF16 = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
-FUSE_AUTO, FUSE_NONE, FUSE_ENCODER, FUSE_LOSS = 0, 1, 2, 4
+FUSE_AUTO, FUSE_NONE, FUSE_ENCODER, FUSE_LOSS, FUSE_NOFOLD_IDX, FUSE_NOFOLD_ACT = 0, 1, 2, 4, 8, 16
 LOSS_DEFAULT, LOSS_HUBER, LOSS_MSE, LOSS_JOINT_MSE = 0, 1, 2, 3
 (T_IDX_EMB, T_ENC_W, T_ENC_B, T_ACT_TABLE, T_SDEC_W, T_SDEC_B, T_RDEC_W, T_RDEC_B, T_RLIN_W, T_RLIN_B, T_ACTENC_W,
  T_ACTENC_B) = range(12)
@@ -41,7 +41,7 @@ class MfvaeArenas(C.Structure):
 class MfvaeBatch(C.Structure):
     _fields_ = [("d_obs", C.c_void_p), ("d_act", C.c_void_p), ("d_next", C.c_void_p), ("d_rew", C.c_void_p),
                 ("d_idx", C.c_void_p), ("d_eps", C.c_void_p), ("batch", C.c_int32), ("sample0", C.c_int64),
-                ("batch_global", C.c_int64), ("seed", C.c_uint64), ("step", C.c_uint64)]
+                ("batch_global", C.c_int64), ("seed", C.c_uint64), ("step", C.c_uint64), ("obs_bf16", C.c_int32), ("next_bf16", C.c_int32)]
 
 
 class MfvaeGemmTiming(C.Structure):

@@ -32,7 +32,39 @@ static inline int grid_for(int64_t work_items, int per_sm = 8) {
 // grid = (row chunks, A); block = 256 threads = (256 / VL) rows x VL column strips of 4.  A thread keeps its strip and
 // walks the rows four at a time: the strip's role (embedding / interior of the observation / edge) and the load width its
 // alignment allows are fixed per thread, so the four rows' loads are straight-line and in flight together.
-template <typename T>
+// 4 consecutive input columns starting at `src`, by the widest access its alignment class `mode` allows
+// (fp32: 3 = 16 B, 2 = 8 B, 1 = 4 B;  bf16: 3 = 8 B, 2 = 4 B, 1 = 2 B)
+template <typename TI> __device__ __forceinline__ void load_in4(const TI* src, int mode, float (&v)[4]);
+template <> __device__ __forceinline__ void load_in4<float>(const float* src, int mode, float (&v)[4]) {
+  if (mode == 3) {
+    const float4 t = ldg_stream4(src);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if (mode == 2) {
+    const float2 t0 = __ldg(reinterpret_cast<const float2*>(src)), t1 = __ldg(reinterpret_cast<const float2*>(src) + 1);
+    v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+  } else {
+    v[0] = __ldg(src); v[1] = __ldg(src + 1); v[2] = __ldg(src + 2); v[3] = __ldg(src + 3);
+  }
+}
+template <> __device__ __forceinline__ void load_in4<__nv_bfloat16>(const __nv_bfloat16* src, int mode, float (&v)[4]) {
+  if (mode == 3) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(src));
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  } else if (mode == 2) {
+    const uint32_t r0 = __ldg(reinterpret_cast<const uint32_t*>(src)), r1 = __ldg(reinterpret_cast<const uint32_t*>(src) + 1);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r0)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r1));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __bfloat162float(src[k]);
+  }
+}
+template <typename TI> __device__ __forceinline__ float load_in1(const TI* p);
+template <> __device__ __forceinline__ float load_in1<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float load_in1<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T, typename TI>
 __global__ void __launch_bounds__(kThreads) stage_kernel(StageArgs p) {
   const int a = blockIdx.y;
   const int nvec = p.x0_ld / 4;
@@ -46,24 +78,19 @@ __global__ void __launch_bounds__(kThreads) stage_kernel(StageArgs p) {
   for (int strip = strip0; strip < nvec; strip += VL) {
     const int c0 = strip * 4;
     const bool interior = c0 >= p.I && c0 + 3 < p.I + od;
-    const float* src0 = p.obs + off + (c0 - p.I);
+    const TI* src0 = static_cast<const TI*>(p.obs) + off + (c0 - p.I);
     // row pitch and base decide the widest aligned load for every row of this strip
-    const uintptr_t al = reinterpret_cast<uintptr_t>(src0) | (static_cast<uintptr_t>(p.obs_ld) << 2);
-    const int mode = !interior ? 0 : ((al & 15) == 0 ? 3 : ((al & 7) == 0 ? 2 : 1));
+    const uintptr_t al = reinterpret_cast<uintptr_t>(src0) | (static_cast<uintptr_t>(p.obs_ld) * sizeof(TI));
+    constexpr uintptr_t W = 4 * sizeof(TI);                      // bytes of 4 input columns
+    const int mode = !interior ? 0 : ((al & (W - 1)) == 0 ? 3 : ((al & (W / 2 - 1)) == 0 ? 2 : 1));
     for (int b = blockIdx.x * rows_per_pass + rphase; b < p.B; b += U * rstep) {
       float v[U][4];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int bb = min(b + u * rstep, p.B - 1);                 // clamped rows are loaded twice, stored once
-        const float* src = src0 + static_cast<int64_t>(bb) * p.obs_ld;
-        if (mode == 3) {
-          const float4 t = ldg_stream4(src);
-          v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w;
-        } else if (mode == 2) {
-          const float2 t0 = __ldg(reinterpret_cast<const float2*>(src)), t1 = __ldg(reinterpret_cast<const float2*>(src) + 1);
-          v[u][0] = t0.x; v[u][1] = t0.y; v[u][2] = t1.x; v[u][3] = t1.y;
-        } else if (mode == 1) {
-          v[u][0] = __ldg(src); v[u][1] = __ldg(src + 1); v[u][2] = __ldg(src + 2); v[u][3] = __ldg(src + 3);
+        const TI* src = src0 + static_cast<int64_t>(bb) * p.obs_ld;
+        if (mode != 0) {
+          load_in4<TI>(src, mode, v[u]);
         } else {
           int id = a;
           if (p.idx) id = max(0, min(static_cast<int>(p.idx[static_cast<int64_t>(bb) * p.A + a]), p.A - 1));   // same clamp as the scatter of backward
@@ -72,7 +99,7 @@ __global__ void __launch_bounds__(kThreads) stage_kernel(StageArgs p) {
             const int c = c0 + k;
             float x = 0.f;
             if (c < p.I) x = p.idx_emb[static_cast<int64_t>(id) * p.I + c];
-            else if (c < p.I + od) x = __ldg(src + k);
+            else if (c < p.I + od) x = load_in1<TI>(src + k);
             v[u][k] = x;
           }
         }
@@ -140,8 +167,13 @@ int launch_stage(const StageArgs& a, cudaStream_t s, bool do_x0, bool do_act) {
   const int chunks = std::max(1, std::min((a.B + rpp * 4 - 1) / (rpp * 4), std::max(1, kNumSMs * 16 / a.A)));
   dim3 sgrid(chunks, a.A);
   if (do_x0) {
-    if (a.dtype == kBF16) stage_kernel<__nv_bfloat16><<<sgrid, kThreads, 0, s>>>(a);
-    else                  stage_kernel<float><<<sgrid, kThreads, 0, s>>>(a);
+    if (a.obs_dtype == kBF16) {
+      if (a.dtype == kBF16) stage_kernel<__nv_bfloat16, __nv_bfloat16><<<sgrid, kThreads, 0, s>>>(a);
+      else                  stage_kernel<float, __nv_bfloat16><<<sgrid, kThreads, 0, s>>>(a);
+    } else {
+      if (a.dtype == kBF16) stage_kernel<__nv_bfloat16, float><<<sgrid, kThreads, 0, s>>>(a);
+      else                  stage_kernel<float, float><<<sgrid, kThreads, 0, s>>>(a);
+    }
     MFVAE_LAUNCH_CHECK();
   }
   if (do_act) {
@@ -304,7 +336,7 @@ __global__ void __launch_bounds__(kThreads) recon_loss_kernel(ReconLossArgs p) {
       const int64_t b = i / wq;
       const int c = static_cast<int>(i - b * wq) * 4;
       const float4 r = p.recon16 ? load4<__nv_bfloat16>(p.recon16 + b * p.grad_ld + c) : ldg_stream4(p.recon + b * p.recon_ld + c);
-      const float4 t = ldg_stream4(p.target + b * p.target_ld + c);
+      const float4 t = p.target16 ? load4<__nv_bfloat16>(p.target16 + b * p.target_ld + c) : ldg_stream4(p.target + b * p.target_ld + c);
       float4 g; float v0, v1, v2, v3;
       recon_elem(r.x, t.x, p.huber, p.grad_scale, v0, g.x);
       recon_elem(r.y, t.y, p.huber, p.grad_scale, v1, g.y);
@@ -321,7 +353,8 @@ __global__ void __launch_bounds__(kThreads) recon_loss_kernel(ReconLossArgs p) {
       const int c = static_cast<int>(i - b * p.width);
       float v, g;
       const float r = p.recon16 ? __bfloat162float(p.recon16[b * p.grad_ld + c]) : p.recon[b * p.recon_ld + c];
-      recon_elem(r, p.target[b * p.target_ld + c], p.huber, p.grad_scale, v, g);
+      const float t = p.target16 ? __bfloat162float(p.target16[b * p.target_ld + c]) : p.target[b * p.target_ld + c];
+      recon_elem(r, t, p.huber, p.grad_scale, v, g);
       acc += v;
       if (grad) grad[b * p.grad_ld + c] = from_f<T>(g);
     }
@@ -332,7 +365,7 @@ __global__ void __launch_bounds__(kThreads) recon_loss_kernel(ReconLossArgs p) {
 
 int launch_recon_loss(const ReconLossArgs& a, cudaStream_t s) {
   const bool vec = a.width % 4 == 0 && (a.recon16 || a.recon_ld % 4 == 0) && a.target_ld % 4 == 0 && a.grad_ld % 4 == 0 &&
-                   (reinterpret_cast<uintptr_t>(a.recon16 ? static_cast<const void*>(a.recon16) : static_cast<const void*>(a.recon)) % 16 == 0) && (reinterpret_cast<uintptr_t>(a.target) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(a.recon16 ? static_cast<const void*>(a.recon16) : static_cast<const void*>(a.recon)) % 16 == 0) && (reinterpret_cast<uintptr_t>(a.target16 ? static_cast<const void*>(a.target16) : static_cast<const void*>(a.target)) % 16 == 0) &&
                    (reinterpret_cast<uintptr_t>(a.grad) % 16 == 0);
   const int64_t items = vec ? a.B * (a.width / 4) : a.B * a.width;
   const int grid = grid_for(items);

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmOp op) {
 
   const T* A = static_cast<const T*>(op.A) + g * op.a_gs;
   const T* B = static_cast<const T*>(op.B) + g * op.b_gs;
+  const T* B2 = op.B2 ? static_cast<const T*>(op.B2) + g * op.b2_gs : nullptr;
 
   float acc[4][4];
 #pragma unroll
@@ -62,7 +63,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmOp op) {
 
   for (int k0 = kbeg; k0 < kend; k0 += TK) {
     load_tile<T>(As, A, op.a_rs, op.a_cs, m0, op.M, k0, kend, tid);
-    load_tile<T>(Bs, B, op.b_rs, op.b_cs, n0, op.N, k0, kend, tid);
+    if (B2 && k0 >= op.k_split) load_tile<T>(Bs, B2, op.b2_rs, 1, n0, op.N, k0 - op.k_split, min(kend - op.k_split, op.k2), tid);
+    else if (B2)                load_tile<T>(Bs, B, op.b_rs, op.b_cs, n0, op.N, k0, min(kend, op.k1), tid);
+    else                        load_tile<T>(Bs, B, op.b_rs, op.b_cs, n0, op.N, k0, kend, tid);
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < TK; ++k) {
@@ -103,6 +106,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmOp op) {
 int gemm_simt(const GemmOp& op, cudaStream_t s) {
   MFVAE_CHECK(op.M > 0 && op.N > 0 && op.K > 0 && op.G > 0, "gemm_simt: empty problem");
   MFVAE_CHECK(op.split_k >= 1, "gemm_simt: split_k >= 1");
+  MFVAE_CHECK(!op.B2 || (op.k_split % 64 == 0 && op.k_split > 0 && op.k_split < op.K && op.b_cs == 1), "gemm_simt: second B segment needs a K-major B and k_split % 64 == 0");
+  MFVAE_CHECK(!op.B2 || (op.k1 > 0 && op.k1 <= op.k_split && op.K == op.k_split + op.k2), "gemm_simt: second B segment: K = k_split + k2, k1 <= k_split");
   MFVAE_CHECK(op.split_k == 1 || op.epi == kEpiAccum, "gemm_simt: split-K needs the accumulate epilogue");
   MFVAE_CHECK(op.epi != kEpiAccum || op.c_dtype == kF32, "gemm_simt: accumulate epilogue needs fp32 C");
   MFVAE_CHECK(op.epi != kEpiReluMask || op.aux, "gemm_simt: relu-mask epilogue needs aux");

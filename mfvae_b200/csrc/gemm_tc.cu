@@ -52,6 +52,7 @@ struct TcParams {
   const __nv_bfloat16* aux; long long aux_gs, aux_ld;
   int accumulate_atomic;                  // split-K: red.global.add.f32
   int c_v8, aux_v8;                       // C rows / aux rows are 32-byte aligned: 256-bit accesses, one sector per lane
+  int kb_switch;                          // > 0: k-blocks >= kb_switch read the B operand through map_b2 (second K segment)
   // kEpiLossGrad: C = d loss / d (A B^T + bias) against `tgt`, loss value accumulated per epilogue warp
   const float* tgt; long long tgt_ld; float grad_scale; int huber; float* loss_partials;
 };
@@ -250,7 +251,8 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, int g, int row
 // ------------------------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN, int CPS>
 __global__ void __launch_bounds__(TcShape<CPS>::kThreads, CPS)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_b2, const TcParams p) {
   using Cfg = TcCfg<BN, CPS>;
   constexpr int kEpiWarps = TcShape<CPS>::kEpiWarps;
   constexpr int kStages = Cfg::kStages;
@@ -271,6 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a); prefetch_tmap(&map_b);
+    if (p.kb_switch > 0) prefetch_tmap(&map_b2);
     for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, kEpiWarps); }
     fence_barrier_init();
@@ -314,6 +317,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (B_MN) {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) tma_load_3d(sb + j * 8192, &map_b, full + stage, nt * BN + j * 64, kb * BK, g);
+          } else if (p.kb_switch > 0 && kb >= p.kb_switch) {
+            tma_load_3d(sb, &map_b2, full + stage, (kb - p.kb_switch) * BK, nt * BN, g);
           } else {
             tma_load_3d(sb, &map_b, full + stage, kb * BK, nt * BN, g);
           }
@@ -460,7 +465,7 @@ int encode_tmap_bf16_3d(CUtensorMap* map, const void* base, int64_t inner, int64
 struct TcPlan {
   GemmOp op;
   TcParams prm;
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_b2;
   int BN = 0; bool a_mn = false, b_mn = false;
   int cps = 1;                // CTAs per SM of the chosen launch shape
   int grid = 0;
@@ -508,7 +513,7 @@ static int launch_tc(const TcPlan* pl, cudaStream_t s) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  MFVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->map_a, pl->map_b, pl->prm));
+  MFVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->map_a, pl->map_b, pl->map_b2, pl->prm));
   MFVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -596,7 +601,19 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
   pl->BN = BN;
   pl->grid = static_cast<int>(std::min<long long>(p.total_work, static_cast<long long>(kNumSMs - g_tc_sm_reserve) * pl->cps));
   int rc = encode_operand(&pl->map_a, op.A, op.M, op.K, op.G, op.a_gs, op.a_rs, op.a_cs, BM, &pl->a_mn);
-  if (rc == 0) rc = encode_operand(&pl->map_b, op.B, op.N, op.K, op.G, op.b_gs, op.b_rs, op.b_cs, BN, &pl->b_mn);
+  p.kb_switch = 0;
+  pl->map_b2 = pl->map_a;                  // placeholder when there is no second segment (never dereferenced)
+  if (op.B2) {
+    if (!(op.b_cs == 1 && op.k_split % BK == 0 && op.k_split > 0 && op.k1 > 0 && op.k1 <= op.k_split && op.K == op.k_split + op.k2 && op.split_k == 1)) {
+      delete pl; MFVAE_FAIL("tcgen05 GEMM: second B segment needs a K-major B, k_split % 64 == 0, K = k_split + k2, no split-K");
+    }
+    bool mn2 = false;
+    if (rc == 0) rc = encode_operand(&pl->map_b, op.B, op.N, op.k1, op.G, op.b_gs, op.b_rs, 1, BN, &pl->b_mn);
+    if (rc == 0) rc = encode_operand(&pl->map_b2, op.B2, op.N, op.k2, op.G, op.b2_gs, op.b2_rs, 1, BN, &mn2);
+    p.kb_switch = op.k_split / BK;
+  } else if (rc == 0) {
+    rc = encode_operand(&pl->map_b, op.B, op.N, op.K, op.G, op.b_gs, op.b_rs, op.b_cs, BN, &pl->b_mn);
+  }
   if (rc != 0) { delete pl; return rc; }
   *out = pl;
   return 0;

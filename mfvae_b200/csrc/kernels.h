@@ -11,7 +11,7 @@ static inline size_t dtype_size(int dt) { return dt == kBF16 ? 2 : 4; }
 
 // ---- bandwidth-bound kernels (elementwise.cu) -------------------------------------------------
 struct StageArgs {
-  const float* obs; int obs_ld;          // [B, S]
+  const void* obs; int obs_ld; int obs_dtype;   // [B, S] fp32 (kF32) or bf16 (kBF16)
   const float* act; int act_ld;          // [B, A] fp32-coded
   const float* idx;                      // [B, A] fp32-coded or nullptr
   const float* idx_emb;                  // [A, I] fp32 master
@@ -54,6 +54,7 @@ struct ReconLossArgs {
   const float* recon; int64_t recon_ld;
   const __nv_bfloat16* recon16;                  // when set: the reconstruction in bf16 (same ld as grad; may alias grad: in-place)
   const float* target; int64_t target_ld;
+  const __nv_bfloat16* target16;                 // when set: the target in bf16 (same ld), `target` is ignored
   void* grad; int64_t grad_ld; int grad_dtype;   // may be nullptr (forward value only)
   int64_t B; int width;
   int huber;
@@ -92,6 +93,17 @@ int launch_philox_normal(float* out, int64_t B, int width, uint64_t seed, uint64
 int launch_loss_total(float* losses, float s_weight, float r_weight, float kl_weight, cudaStream_t s, const float* partials = nullptr,
                       int n_partials = 0, float partial_scale = 0.f);
 
+// ---- folded constant-input column blocks (fold.cu) ---------------------------------------------
+int launch_onehot(const float* act, int act_ld, const int32_t* n_act, void* zin, int dtype, int64_t zin_ld, int col0, int A, int nmax,
+                  int width, int64_t B, cudaStream_t s);
+int launch_act_fold_fwd(const float* W0, int64_t w_ld, int wcol0, const float* table, int64_t table_gs, void* Tt, int dtype, int64_t t_ld,
+                        int rows, int A, int C, int nmax, cudaStream_t s);
+int launch_act_fold_bwd(const float* dT, int64_t t_ld, const float* W0, float* gW0, int64_t w_ld, int wcol0, const float* table, float* gtable,
+                        int64_t table_gs, int rows, int A, int C, int nmax, cudaStream_t s);
+int launch_enc_bias_fold(const float* W0, int64_t w_ld, const float* b0, const float* emb, float* eb, int A, int N, int I, cudaStream_t s);
+int launch_emb_grad_fold(const float* W0, float* gW0, int64_t w_ld, const float* db0, const float* emb, float* g_emb, int A, int N, int I,
+                         cudaStream_t s);
+
 // ---- GEMM (gemm_simt.cu / gemm_tc.cu) --------------------------------------------------------
 enum Epilogue { kEpiNone = 0, kEpiBias = 1, kEpiBiasRelu = 2, kEpiReluMask = 3, kEpiAccum = 4, kEpiLossGrad = 5 };
 
@@ -100,6 +112,10 @@ struct GemmOp {
   int dtype = kF32;                           // operand type
   const void* A = nullptr; int64_t a_gs = 0, a_rs = 0, a_cs = 0;   // A(m,k)
   const void* B = nullptr; int64_t b_gs = 0, b_rs = 0, b_cs = 0;   // B(n,k)
+  // optional second K segment of the B operand (K-major only): for k >= k_split, B(n,k) = B2(n, k - k_split).  k_split must
+  // be a multiple of 64.  Lets a Linear layer read part of its weight columns from a derived table (decoder layer 0:
+  // [W0 z-columns | W0_act . action tables]) without materialising the concatenation.
+  const void* B2 = nullptr; int64_t b2_gs = 0, b2_rs = 0; int k_split = 0, k1 = 0, k2 = 0;   // k1 / k2 = valid columns of B / B2 (K = k_split + k2)
   void* C = nullptr; int64_t c_gs = 0, c_ld = 0; int c_dtype = kF32;
   const float* bias = nullptr; int64_t bias_gs = 0;
   int epi = kEpiNone;

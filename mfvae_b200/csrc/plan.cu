@@ -43,6 +43,9 @@ struct MfvaeHandle_ {
   float s_weight = 1.0f;                     // weight of the state reconstruction term (1 in torch_ver; 1 - r_weight in jax_ver)
   bool cont_act = false; int Hact = 64, Kap = 8, act_total = 0;   // continuous actions: ActionEncoder D_a -> Hact -> C
   std::vector<int32_t> act_off;
+  // folded constant-input column blocks (fold.cu): discrete actions -> one-hot columns against T = W0_act . tables;
+  // codebook agent index -> per-agent bias of encoder layer 0
+  bool fold_act = false; int Kz = 0, Kzp = 0, Koh = 0, Kohp = 0, K0f = 0;
   int ne = 0, nd = 0;                       // number of Linear layers in encoder / decoder
   std::vector<int> encN, encK;              // per encoder layer (K padded)
   std::vector<int> decH;                    // decoder hidden widths
@@ -65,6 +68,7 @@ struct MfvaeHandle_ {
   char* ws = nullptr; int64_t ws_bytes = 0; int B = 0;
   struct Buf { int64_t off = 0; int64_t ld = 0; int64_t gs = 0; };
   Buf X0, LAT, ZIN, RS, RR0, RR, DRS, DRR, DRR0, GZIN, DLAT, GX0, ACT0, HA, DHA;
+  Buf X0F, TACT, DTACT, EB0;                  // folded paths: X0F[A][B][K0f] = [obs | 0]; TACT / DTACT [2 H0][Kohp]; EB0[A][N0] fp32
   std::vector<Buf> XE, DXE, HD, DHD;
   int64_t off_losses = 0, off_scratch = 0;
 
@@ -78,6 +82,9 @@ struct MfvaeHandle_ {
   int g_sout_fwd16 = -1;                     // train step: recon_s written once, in bf16, into the D(recon_s) buffer (loss runs in place)                      // state output layer with the reconstruction loss + its gradient as the epilogue
   int g_act_fwd1 = -1, g_act_fwd2 = -1, g_act_wg2 = -1, g_act_dg2 = -1, g_act_wg1 = -1;
   int g_sout_wg = -1, g_sout_dg = -1, g_rout_wg = -1, g_rout_dg = -1, g_rl_wg = -1, g_rl_dg = -1;
+  int g_dec_wgT = -1;                        // d T = d H0^T . onehot(act)            (fold_act)
+  int g_enc_fwd0_f = -1, g_enc_wg0_f = -1;   // encoder layer 0 on [obs | 0] with the folded bias (codebook agent index)
+  cudaEvent_t eb_ev = nullptr;               // folded encoder bias is ready (aux stream)
 
   // side stream for the wgrad / bias-gradient chain of backward, with its fork / join events
   cudaStream_t side = nullptr;
@@ -131,6 +138,10 @@ static int build_layout(MfvaeHandle_* h) {
   h->Ip = h->I;
   h->K0p = static_cast<int>(round_up(h->I + maxo, 8));
   h->Din = h->A * (h->L + h->C);
+  h->fold_act = (c.continuous_act == 0) && !(c.fusion & MFVAE_FUSE_NOFOLD_ACT);
+  h->Kz = h->A * h->L; h->Kzp = static_cast<int>(round_up(h->Kz, 64));
+  h->Koh = h->A * h->nact_max; h->Kohp = static_cast<int>(round_up(h->Koh, 8));
+  h->K0f = h->K0p - h->I;
   h->ne = c.n_enc_hidden + 1; h->nd = c.n_dec_hidden + 1;
   h->encN.clear(); h->encK.clear(); h->decH.clear();
   for (int l = 0; l < h->ne; ++l) {
@@ -235,7 +246,7 @@ static int64_t layout_workspace(MfvaeHandle_* h, int B) {
   h->XE.clear(); h->DXE.clear(); h->HD.clear(); h->DHD.clear();
   for (int l = 0; l + 1 < h->ne; ++l) h->XE.push_back(mk(A, h->encN[l], es, true));
   h->LAT = mk(A, 2 * h->L, 4, true);
-  h->ZIN = mk(1, h->Din, es, false);
+  h->ZIN = mk(1, h->fold_act ? h->Kzp + h->Kohp : h->Din, es, false);
   for (int l = 0; l < h->cfg.n_dec_hidden; ++l) h->HD.push_back(mk(1, 2 * h->decH[l], es, false));
   h->RS = mk(1, h->Sp, 4, false);
   h->RR0 = mk(1, h->Ap, es, false);
@@ -244,11 +255,18 @@ static int64_t layout_workspace(MfvaeHandle_* h, int B) {
   h->DRR = mk(1, h->Ap, es, false);
   h->DRR0 = mk(1, h->Ap, es, false);
   for (int l = 0; l < h->cfg.n_dec_hidden; ++l) h->DHD.push_back(mk(1, 2 * h->decH[l], es, false));
-  h->GZIN = mk(1, h->Din, es, false);
+  h->GZIN = mk(1, h->fold_act ? h->Kzp : h->Din, es, false);
   h->DLAT = mk(A, 2 * h->L, es, true);
   for (int l = 0; l + 1 < h->ne; ++l) h->DXE.push_back(mk(A, h->encN[l], es, true));
   h->GX0 = mk(A, h->Ip, es, true);
   if (h->cont_act) { h->ACT0 = mk(A, h->Kap, es, true); h->HA = mk(A, h->Hact, es, true); h->DHA = mk(A, h->Hact, es, true); }
+  h->X0F = mk(A, h->K0f, es, true);
+  if (h->fold_act) {
+    const int64_t rows = 2LL * h->decH[0];
+    h->TACT.ld = h->Kohp; h->TACT.gs = 0; h->TACT.off = alloc(rows * h->Kohp * es);
+    h->DTACT.ld = h->Kohp; h->DTACT.gs = 0; h->DTACT.off = alloc(rows * h->Kohp * 4);
+  }
+  h->EB0.ld = h->encN[0]; h->EB0.gs = h->encN[0]; h->EB0.off = alloc(static_cast<int64_t>(A) * h->encN[0] * 4);
   h->off_losses = alloc(64 * sizeof(float));
   h->off_scratch = alloc(3 * 4096 * sizeof(float));
   return cur;
@@ -291,14 +309,18 @@ static int build_ops(MfvaeHandle_* h) {
     return push(o);
   };
   // dW[g] (N_out x K_in) += D[g]^T (N_out x B) * X[g] (B x K_in)
-  auto wgrad = [&](int G, int Nout, int Kin, const void* D, int64_t d_gs, int64_t d_ld, const void* X, int64_t x_gs, int64_t x_ld,
-                   int64_t gw_off, int64_t gw_gs, int64_t gw_ld) {
+  auto wgrad_to = [&](int G, int Nout, int Kin, const void* D, int64_t d_gs, int64_t d_ld, const void* X, int64_t x_gs, int64_t x_ld,
+                      float* out, int64_t gw_gs, int64_t gw_ld) {
     GemmOp o; o.G = G; o.M = Nout; o.N = Kin; o.K = B; o.dtype = dt;
     o.A = D; o.a_gs = d_gs; o.a_rs = 1; o.a_cs = d_ld;
     o.B = X; o.b_gs = x_gs; o.b_rs = 1; o.b_cs = x_ld;
-    o.C = Gd + gw_off; o.c_gs = gw_gs; o.c_ld = gw_ld; o.c_dtype = kF32;
+    o.C = out; o.c_gs = gw_gs; o.c_ld = gw_ld; o.c_dtype = kF32;
     o.epi = kEpiAccum; o.split_k = pick_split_k(G, Nout, Kin, B);
     return push(o);
+  };
+  auto wgrad = [&](int G, int Nout, int Kin, const void* D, int64_t d_gs, int64_t d_ld, const void* X, int64_t x_gs, int64_t x_ld,
+                   int64_t gw_off, int64_t gw_gs, int64_t gw_ld) {
+    return wgrad_to(G, Nout, Kin, D, d_gs, d_ld, X, x_gs, x_ld, Gd + gw_off, gw_gs, gw_ld);
   };
   // dX[g] (B x K_in) = D[g] (B x N_out) * W[g] (N_out x K_in)  [* (mask > 0)]
   auto dgrad = [&](int G, int Kin, int Nout, const void* D, int64_t d_gs, int64_t d_ld, const void* Wt, int64_t w_gs, int64_t w_ld,
@@ -334,6 +356,16 @@ static int build_ops(MfvaeHandle_* h) {
                                   buf(dx), dx.gs, dx.ld, buf(in), in.gs, in.ld));
     }
   }
+  // encoder layer 0 with the id-embedding folded into a per-agent bias (fold.cu): input [obs | 0], weight columns [I, K0p)
+  {
+    const int N = h->encN[0], K = h->encK[0], I = h->I;
+    const MfvaeHandle_::Buf& out = (h->ne == 1) ? h->LAT : h->XE[0];
+    const MfvaeHandle_::Buf& D = (h->ne == 1) ? h->DLAT : h->DXE[0];
+    const float* eb = reinterpret_cast<const float*>(ws + h->EB0.off);
+    h->g_enc_fwd0_f = fwd(A, B, N, h->K0f, buf(h->X0F), h->X0F.gs, h->X0F.ld, wptr(h->encW[0].off + I), static_cast<int64_t>(N) * K, K,
+                          buf(out), out.gs, out.ld, (h->ne == 1) ? kF32 : dt, eb, N, h->ne > 1);
+    h->g_enc_wg0_f = wgrad(A, N, h->K0f, buf(D), D.gs, D.ld, buf(h->X0F), h->X0F.gs, h->X0F.ld, h->encW[0].off + I, static_cast<int64_t>(N) * K, K);
+  }
   // ---- ActionEncoder (continuous actions, G = A): D_a -> Hact (ReLU) -> C, written straight into its ZIN columns ----
   if (h->cont_act) {
     const int Hh = h->Hact, C = h->C, Kap = h->Kap;
@@ -353,7 +385,19 @@ static int build_ops(MfvaeHandle_* h) {
   const int nh = h->cfg.n_dec_hidden;
   for (int l = 0; l < nh; ++l) {
     const int H = h->decH[l];
-    if (l == 0) {
+    if (l == 0 && h->fold_act) {
+      // [z | 0 | onehot(act)] . [W0 z-columns | T]^T: the action-embedding columns are K = A*n_act one-hot columns (fold.cu)
+      const int i0 = fwd(1, B, 2 * H, h->Kzp + h->Koh, buf(h->ZIN), 0, h->ZIN.ld, wptr(h->decW[0].off), 0, h->Din,
+                         buf(h->HD[0]), 0, h->HD[0].ld, dt, P + h->decB[0].off, 0, true);
+      GemmOp& o = h->gemms[i0];
+      o.B2 = ws + h->TACT.off; o.b2_gs = 0; o.b2_rs = h->TACT.ld; o.k_split = h->Kzp; o.k1 = h->Kz; o.k2 = h->Koh;
+      h->g_dec_fwd.push_back(i0);
+      h->g_dec_wg.push_back(wgrad(1, 2 * H, h->Kz, buf(h->DHD[0]), 0, h->DHD[0].ld, buf(h->ZIN), 0, h->ZIN.ld, h->decW[0].off, 0, h->Din));
+      h->g_dec_wgT = wgrad_to(1, 2 * H, h->Koh, buf(h->DHD[0]), 0, h->DHD[0].ld, ws + h->ZIN.off + static_cast<int64_t>(h->Kzp) * es, 0, h->ZIN.ld,
+                              reinterpret_cast<float*>(ws + h->DTACT.off), 0, h->DTACT.ld);
+      h->g_dec_dg.push_back(dgrad(1, h->Kz, 2 * H, buf(h->DHD[0]), 0, h->DHD[0].ld, wptr(h->decW[0].off), 0, h->Din,
+                                  buf(h->GZIN), 0, h->GZIN.ld, nullptr, 0, 0));
+    } else if (l == 0) {
       h->g_dec_fwd.push_back(fwd(1, B, 2 * H, h->Din, buf(h->ZIN), 0, h->ZIN.ld, wptr(h->decW[0].off), 0, h->Din,
                                  buf(h->HD[0]), 0, h->HD[0].ld, dt, P + h->decB[0].off, 0, true));
       h->g_dec_wg.push_back(wgrad(1, 2 * H, h->Din, buf(h->DHD[0]), 0, h->DHD[0].ld, buf(h->ZIN), 0, h->ZIN.ld,
@@ -441,6 +485,14 @@ static bool use_aux(const MfvaeHandle_* h) { return h->aux != nullptr && !h->pro
 
 // action-embedding half of the decoder input: independent of the encoders, so it runs beside them on the aux stream
 static int act_embed_on(MfvaeHandle_* h, const StageArgs& st, cudaStream_t q) {
+  if (h->fold_act) {
+    // one-hot action columns + T = W0_act . tables (from the fp32 masters, every step: both factors train)
+    MFVAE_TRY(launch_onehot(st.act, st.act_ld, h->d_meta + 2 * h->A, h->ws + h->ZIN.off, h->dtype, h->ZIN.ld, h->Kzp, h->A, h->nact_max,
+                            h->Kohp, h->B, q));
+    return launch_act_fold_fwd(h->ar.d_param + h->decW[0].off, h->Din, h->Kz, h->ar.d_param + h->actT.off,
+                               static_cast<int64_t>(h->nact_max) * h->C, h->ws + h->TACT.off, h->dtype, h->TACT.ld, 2 * h->decH[0], h->A, h->C,
+                               h->nact_max, q);
+  }
   if (!h->cont_act) return launch_stage(st, q, false, true);
   // ActionEncoder MLP (reference model.py:148)
   MFVAE_TRY(launch_stage_actions(st.act, h->act_total, h->d_meta + 3 * h->A, h->d_meta + 2 * h->A, h->ws + h->ACT0.off, h->dtype,
@@ -449,10 +501,26 @@ static int act_embed_on(MfvaeHandle_* h, const StageArgs& st, cudaStream_t q) {
   return run_gemm(h, h->g_act_fwd2, q);
 }
 
-static int do_forward_act_embed(MfvaeHandle_* h, const StageArgs& st, cudaStream_t s) {
-  if (!use_aux(h)) return act_embed_on(h, st, s);
+// encoder layer 0 reads [obs | 0] and a per-agent bias b0 + W0[:, :I] . emb[a] when the batch carries the codebook agent index
+static bool fold_idx(const MfvaeHandle_* h, const MfvaeBatch* b) {
+  return b->d_idx == nullptr && h->enc_fused == nullptr && !(h->cfg.fusion & MFVAE_FUSE_NOFOLD_IDX);
+}
+static int enc_bias_on(MfvaeHandle_* h, cudaStream_t q) {
+  return launch_enc_bias_fold(h->ar.d_param + h->encW[0].off, h->encK[0], h->ar.d_param + h->encB[0].off, h->ar.d_param + h->idx_emb.off,
+                              reinterpret_cast<float*>(h->ws + h->EB0.off), h->A, h->encN[0], h->I, q);
+}
+
+static int do_forward_act_embed(MfvaeHandle_* h, const StageArgs& st, cudaStream_t s, bool fold_i) {
+  if (!use_aux(h)) {
+    if (fold_i) MFVAE_TRY(enc_bias_on(h, s));
+    return act_embed_on(h, st, s);
+  }
   MFVAE_CUDA(cudaEventRecord(h->aux_fork_ev, s));          // orders it after whatever last read ZIN on the caller's stream
   MFVAE_CUDA(cudaStreamWaitEvent(h->aux, h->aux_fork_ev, 0));
+  if (fold_i) {
+    MFVAE_TRY(enc_bias_on(h, h->aux));
+    MFVAE_CUDA(cudaEventRecord(h->eb_ev, h->aux));
+  }
   MFVAE_TRY(act_embed_on(h, st, h->aux));
   MFVAE_CUDA(cudaEventRecord(h->aux_join_ev, h->aux));
   return 0;
@@ -495,7 +563,7 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
   MFVAE_TRY(check_ready(h, b));
   const MfvaeBatch* lb = fuse_loss ? b : nullptr;
   StageArgs st{};
-  st.obs = b->d_obs; st.obs_ld = h->S; st.act = b->d_act; st.act_ld = h->cont_act ? h->act_total : h->A; st.idx = b->d_idx;
+  st.obs = b->d_obs; st.obs_ld = h->S; st.obs_dtype = b->obs_bf16 ? kBF16 : kF32; st.act = b->d_act; st.act_ld = h->cont_act ? h->act_total : h->A; st.idx = b->d_idx;
   st.idx_emb = h->ar.d_param + h->idx_emb.off;
   st.act_table = h->cont_act ? nullptr : h->ar.d_param + h->actT.off; st.act_table_gs = static_cast<int64_t>(h->nact_max) * h->C; st.n_act_max = h->nact_max;
   st.obs_off = h->d_meta; st.obs_dim = h->d_meta + h->A; st.n_act = h->d_meta + 2 * h->A;
@@ -509,9 +577,11 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
     out->d_latent = lat; out->d_losses = losses_ptr(h);
     if (fuse_loss || recon16) { out->d_recon_s = nullptr; out->recon_s_ld = 0; }      // not materialised in fp32 on this path
   }
+  const bool fold_i = fold_idx(h, b);
   if (h->enc_fused) {
     // staging of X0, the four encoder layers, reparameterisation and KL: one kernel (enc_fused.cu)
-    MFVAE_TRY(do_forward_act_embed(h, st, s));
+    MFVAE_TRY(do_forward_act_embed(h, st, s, false));
+    MFVAE_CHECK(!b->obs_bf16, "the fused encoder kernel reads fp32 observations");
     EncFwdBatch eb{};
     eb.obs = b->d_obs; eb.obs_ld = h->S; eb.idx = b->d_idx; eb.idx_ld = h->A;
     eb.eps = b->d_eps; eb.eps_ld = static_cast<int64_t>(h->A) * h->L; eb.seed = b->seed; eb.step = b->step; eb.sample0 = b->sample0;
@@ -519,9 +589,15 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
     MFVAE_TRY(enc_fused_forward(h->enc_fused, eb, s));
     return do_forward_decoders(h, s, lb, h->cfg.huber, recon16, defer_reward_join);
   }
-  MFVAE_TRY(do_forward_act_embed(h, st, s));
+  MFVAE_TRY(do_forward_act_embed(h, st, s, fold_i));
+  if (fold_i) {       // X0F[a][b][:] = [obs_a | 0]: the staging kernel with a zero-width embedding block
+    st.I = 0; st.idx = nullptr;
+    st.x0 = h->ws + h->X0F.off; st.x0_ld = static_cast<int>(h->X0F.ld); st.x0_gs = h->X0F.gs;
+  }
   MFVAE_TRY(launch_stage(st, s, true, false));
-  for (int l = 0; l < h->ne; ++l) MFVAE_TRY(run_gemm(h, h->g_enc_fwd[l], s));
+  if (fold_i && use_aux(h)) MFVAE_CUDA(cudaStreamWaitEvent(s, h->eb_ev, 0));
+  MFVAE_TRY(run_gemm(h, fold_i ? h->g_enc_fwd0_f : h->g_enc_fwd[0], s));
+  for (int l = 1; l < h->ne; ++l) MFVAE_TRY(run_gemm(h, h->g_enc_fwd[l], s));
   ReparamArgs rp{};
   rp.mu = lat; rp.lv = lat + h->L; rp.lat_as = h->LAT.gs; rp.lat_bs = h->LAT.ld;
   rp.eps = b->d_eps; rp.eps_ld = static_cast<int64_t>(h->A) * h->L;
@@ -545,6 +621,7 @@ static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStre
   a.recon = reinterpret_cast<const float*>(h->ws + h->RS.off); a.recon_ld = h->RS.ld;
   a.recon16 = recon16 ? reinterpret_cast<const __nv_bfloat16*>(h->ws + h->DRS.off) : nullptr;   // in place over D(recon_s)
   a.target = b->d_next; a.target_ld = h->S;
+  a.target16 = b->next_bf16 ? reinterpret_cast<const __nv_bfloat16*>(b->d_next) : nullptr;
   a.grad = h->ws + h->DRS.off; a.grad_ld = h->DRS.ld; a.grad_dtype = h->dtype;
   a.B = h->B; a.width = h->S;
   const double cs = joint_mse ? Bg * (h->S + h->A) : Bg * h->S;
@@ -557,7 +634,7 @@ static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStre
   if (!state_fused) MFVAE_TRY(launch_recon_loss(a, s));
   if (join_reward && use_aux(h)) MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join2_ev, 0));   // reward head (aux stream) is needed from here
   a.recon = reinterpret_cast<const float*>(h->ws + h->RR.off); a.recon_ld = h->RR.ld; a.recon16 = nullptr;
-  a.target = b->d_rew; a.target_ld = h->A;
+  a.target = b->d_rew; a.target_ld = h->A; a.target16 = nullptr;
   a.grad = h->ws + h->DRR.off; a.grad_ld = h->DRR.ld; a.width = h->A;
   a.grad_scale = static_cast<float>(static_cast<double>(rw) / cr); a.loss_scale = static_cast<float>(1.0 / cr);
   a.loss_out = losses_ptr(h) + 2; a.scratch = scratch_ptr(h, 2);
@@ -585,6 +662,8 @@ static int zero_grads(MfvaeHandle_* h, cudaStream_t q) {
     if (end > cur) MFVAE_CUDA(cudaMemsetAsync(G + cur, 0, static_cast<size_t>(end - cur) * sizeof(float), q));
     if (i < ns) cur = skip[i][1];
   }
+  if (h->fold_act && !(h->use_tc && gemm_tc_overwrites(h->tc[h->g_dec_wgT])))
+    MFVAE_CUDA(cudaMemsetAsync(h->ws + h->DTACT.off, 0, static_cast<size_t>(2) * h->decH[0] * h->DTACT.ld * sizeof(float), q));
   return 0;
 }
 
@@ -661,6 +740,13 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
   for (int l = nh - 1; l >= 0; --l) {
     MFVAE_TRY(fork());                                          // D_l (both decoder halves) ready
     MFVAE_TRY(run_gemm(h, h->g_dec_wg[l], w));
+    if (l == 0 && h->fold_act) {
+      // d T = d H0^T . onehot, then exactly: d W0[:, action columns] = d T . tables, d tables = d T^T . W0[:, action columns]
+      MFVAE_TRY(run_gemm(h, h->g_dec_wgT, w));
+      MFVAE_TRY(launch_act_fold_bwd(reinterpret_cast<const float*>(ws + h->DTACT.off), h->DTACT.ld, h->ar.d_param + h->decW[0].off,
+                                    G + h->decW[0].off, h->Din, h->Kz, h->ar.d_param + h->actT.off, G + h->actT.off,
+                                    static_cast<int64_t>(h->nact_max) * h->C, 2 * h->decH[0], A, h->C, h->nact_max, w));
+    }
     MFVAE_TRY(launch_colsum(ws + h->DHD[l].off, dt, 1, h->B, 2 * h->decH[l], h->DHD[l].ld, 0, G + h->decB[l].off, 0, cs));
     if (l == 1) { MFVAE_TRY(csum_into_w()); MFVAE_CUDA(cudaEventRecord(h->buckets[1].ev, w)); }
     MFVAE_TRY(run_gemm(h, h->g_dec_dg[l], s));
@@ -676,7 +762,9 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
     MFVAE_CUDA(cudaStreamWaitEvent(h->aux, h->aux_fork2_ev, 0));
     at = h->aux;
   }
-  if (!h->cont_act) {
+  if (h->fold_act) {
+    // the action tables' gradient came out of act_fold_bwd above
+  } else if (!h->cont_act) {
     MFVAE_TRY(launch_act_table_grad(ws + h->GZIN.off, dt, h->GZIN.ld, A * h->L, b->d_act, A, h->d_meta + 2 * A, A, h->C, h->B,
                                     G + h->actT.off, static_cast<int64_t>(h->nact_max) * h->C, at));
   } else {   // ActionEncoder backward: D = the action columns of d ZIN
@@ -701,15 +789,24 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
   rb.glat = glat;
   MFVAE_TRY(launch_reparam_kl_bwd(rb, s));
   // encoders, last layer to first
+  const bool fold_i = fold_idx(h, b);
   for (int l = h->ne - 1; l >= 0; --l) {
     const MfvaeHandle_::Buf& D = (l + 1 == h->ne) ? h->DLAT : h->DXE[l];
     MFVAE_TRY(fork());
-    MFVAE_TRY(run_gemm(h, h->g_enc_wg[l], w));
+    MFVAE_TRY(run_gemm(h, (l == 0 && fold_i) ? h->g_enc_wg0_f : h->g_enc_wg[l], w));
     MFVAE_TRY(launch_colsum(ws + D.off, dt, A, h->B, h->encN[l], D.ld, D.gs, G + h->encB[l].off, h->encN[l], cs));
-    MFVAE_TRY(run_gemm(h, h->g_enc_dg[l], s));
+    if (l == 0 && fold_i) {
+      // d emb[a] = W0_a[:, :I]^T . d b0_a and d W0_a[:, :I] = d b0_a (x) emb[a], behind the column sum that produces d b0
+      MFVAE_TRY(launch_emb_grad_fold(h->ar.d_param + h->encW[0].off, G + h->encW[0].off, h->encK[0], G + h->encB[0].off,
+                                     h->ar.d_param + h->idx_emb.off, G + h->idx_emb.off, A, h->encN[0], h->I, cs));
+    } else {
+      MFVAE_TRY(run_gemm(h, h->g_enc_dg[l], s));
+    }
   }
   // id embedding (model.py:113,142)
-  if (b->d_idx)
+  if (fold_i) {
+    // done by emb_grad_fold above
+  } else if (b->d_idx)
     MFVAE_TRY(launch_idx_emb_scatter(ws + h->GX0.off, dt, h->GX0.gs, h->GX0.ld, b->d_idx, A, A, h->I, h->B, G + h->idx_emb.off, s));
   else
     MFVAE_TRY(launch_colsum(ws + h->GX0.off, dt, A, h->B, h->I, h->GX0.ld, h->GX0.gs, G + h->idx_emb.off, h->I, s));
@@ -783,6 +880,7 @@ int mfvae_create(const MfvaeConfig* cfg, int device, MfvaeHandle* out) {
   cudaEventCreateWithFlags(&h->zero_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->loss_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->zero_fork_ev, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->eb_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->aux_fork_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->aux_join_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->aux_fork2_ev, cudaEventDisableTiming);
@@ -818,6 +916,7 @@ int mfvae_destroy(MfvaeHandle h) {
   if (h->zero_fork_ev) cudaEventDestroy(h->zero_fork_ev);
   for (auto e : h->csum_ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {h->aux_fork_ev, h->aux_join_ev, h->aux_fork2_ev, h->aux_join2_ev}) if (e) cudaEventDestroy(e);
+  if (h->eb_ev) cudaEventDestroy(h->eb_ev);
   if (h->opt_ev) cudaEventDestroy(h->opt_ev);
   if (h->dec_read_ev) cudaEventDestroy(h->dec_read_ev);
   if (h->opt_stream) cudaStreamDestroy(h->opt_stream);
@@ -922,7 +1021,7 @@ int mfvae_fwd_bwd(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* s
   MFVAE_CHECK(h, "null handle");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // tensor-core engine: reconstruction loss of the state head fused into its output-layer GEMM (recon_s is not written)
-  const bool fuse = h->use_tc && (h->cfg.fusion & MFVAE_FUSE_LOSS) && h->g_sout_loss >= 0 && b && b->d_next && b->d_rew;
+  const bool fuse = h->use_tc && (h->cfg.fusion & MFVAE_FUSE_LOSS) && h->g_sout_loss >= 0 && b && b->d_next && b->d_rew && !b->next_bf16;
   // bf16 engine: the train step needs recon_s only inside the loss, so the output layer writes it once in bf16 straight into
   // the D(recon_s) buffer and the loss kernel turns it into the gradient in place (no fp32 round trip: -140 MB per step)
   const bool r16 = !fuse && h->use_tc && h->g_sout_fwd16 >= 0 && b && b->d_next && b->d_rew;

@@ -90,10 +90,13 @@ class PackedBatch:
     """Device-resident batch in the layout the kernels read: what ``create_dataset``
     (reference trainer.py:7-45) produces, without the per-agent dict indirection.
 
-    obs  [B, S] fp32   observations of all agents concatenated in codebook order
+    obs  [B, S] fp32   observations of all agents concatenated in codebook order; may be bfloat16 (a host ring that keeps
+                       observations in bf16 ships half the PCIe bytes; the bf16 engine rounds them on arrival anyway, so the
+                       step is bit-identical to feeding the fp32 values those bf16 numbers came from)
     act  [B, A] fp32   float-coded discrete action per agent (replay_buffer.py:76); continuous actions:
                        [B, sum(action_dim)] action vectors concatenated in codebook order
-    next [B, S] fp32   next observations (= ``next_states`` target)      (optional)
+    next [B, S] fp32   next observations (= ``next_states`` target)      (optional; bfloat16 allowed: ROUNDS THE TARGET, the
+                       loss moves at the 1e-3 level -- an explicit opt-in of the caller)
     rew  [B, A] fp32   rewards (= ``rewards`` target)                     (optional)
     idx  [B, A] fp32   agent-index column of ``idx_state`` or None = codebook order
     eps  [B, A*L] fp32 explicit normal draw or None = Philox(seed, step, sample0 + row)
@@ -265,7 +268,8 @@ class MAVAE(nn.Module):
         cfg.continuous_act = 0 if descrete_act else 1
         cfg.act_hidden = ActionEncoder.HIDDEN[0]
         cfg.fusion = {"auto": L.FUSE_AUTO, "none": L.FUSE_NONE, "encoder": L.FUSE_ENCODER, "loss": L.FUSE_LOSS,
-                      "encoder+loss": L.FUSE_ENCODER | L.FUSE_LOSS}[fusion]
+                      "encoder+loss": L.FUSE_ENCODER | L.FUSE_LOSS, "nofold": L.FUSE_NONE | L.FUSE_NOFOLD_IDX | L.FUSE_NOFOLD_ACT, "nofold_idx": L.FUSE_NONE | L.FUSE_NOFOLD_IDX,
+                      "nofold_act": L.FUSE_NONE | L.FUSE_NOFOLD_ACT}[fusion]
         self._cfg = cfg
         lib = L.lib()
         self._h = C.c_void_p()
@@ -529,6 +533,11 @@ class MAVAE(nn.Module):
         cb.d_rew = pb.rew.data_ptr() if pb.rew is not None else None
         cb.d_idx = pb.idx.data_ptr() if pb.idx is not None else None
         cb.d_eps = pb.eps.data_ptr() if pb.eps is not None else None
+        cb.obs_bf16 = int(pb.obs.dtype == torch.bfloat16)
+        cb.next_bf16 = int(pb.next is not None and pb.next.dtype == torch.bfloat16)
+        for name, t in (("obs", pb.obs), ("next", pb.next)):
+            if t is not None and (t.dtype not in (torch.float32, torch.bfloat16) or not t.is_contiguous()):
+                raise TypeError(f"mfvae_b200: PackedBatch.{name} must be a contiguous float32 or bfloat16 matrix")
         cb.batch, cb.sample0, cb.batch_global = pb.batch, pb.sample0, pb.batch_global
         cb.seed, cb.step = self.philox_seed, self.philox_step
         return cb
@@ -555,8 +564,14 @@ class MAVAE(nn.Module):
             act = torch.cat([_f32c(actions[a], dev).reshape(-1, 1) for a in keys], dim=1)
             nmax = torch.tensor([float(self.act_dim[a]) for a in keys], device=dev)
             bad = bad | ((act < 0) | (act >= nmax)).any()
-        if bool(bad):
+        # create_dataset (trainer.py:21) writes the codebook index into column 0: row b of agent a carries a.  Then the
+        # id-embedding is a per-agent constant and the engine folds it into encoder layer 0's bias (idx = None).
+        codebook = (idx == torch.arange(A, device=dev, dtype=idx.dtype)).all()
+        bad, codebook = (bool(x) for x in torch.stack([bad, codebook]).cpu())
+        if bad:
             raise IndexError("index out of range in self")
+        if codebook:
+            idx = None
         if not self.descrete_act:       # continuous: [B, act_dim_a] vectors, concatenated in agent order
             act = torch.cat([_f32c(actions[a], dev).reshape(cols[0].shape[0], -1) for a in keys], dim=1).contiguous()
         if eps is not None:

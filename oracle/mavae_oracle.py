@@ -219,40 +219,74 @@ def _q(x, on, fwd=True, bwd=True):
     return _RoundBF16.apply(x, fwd, bwd) if on else x
 
 
-def _mlp(P, prefix: str, n_layers: int, x: torch.Tensor, q: bool = False, out_fwd: bool = False) -> torch.Tensor:
+def _mlp(P, prefix: str, n_layers: int, x: torch.Tensor, q: bool = False, out_fwd: bool = False, first=None) -> torch.Tensor:
+    """``first``: pre-activation of layer 0 computed by the caller (the folded layer-0 forms of ``emulate_bf16``)."""
     names = _linear_names(prefix, n_layers)
     for i, (wn, bn) in enumerate(names):
-        x = torch.nn.functional.linear(x, _q(P[wn], q, True, False), P[bn])      # nn.Linear: x W^T + b
+        if i == 0 and first is not None:
+            x = first
+        else:
+            x = torch.nn.functional.linear(x, _q(P[wn], q, True, False), P[bn])      # nn.Linear: x W^T + b
         if i + 1 < n_layers:
             x = _q(torch.relu(x), q)
     return _q(x, q, out_fwd, True)
 
 
 def forward(P: Dict[str, torch.Tensor], spec: Spec, idx_state: Dict[str, torch.Tensor],
-            actions: Dict[str, torch.Tensor], eps: Dict[str, torch.Tensor], emulate_bf16: bool = False):
+            actions: Dict[str, torch.Tensor], eps: Dict[str, torch.Tensor], emulate_bf16: bool = False, fold: bool = True):
     """``MAVAE.forward`` with the normal draw made explicit.  Returns
-    ``(recon_state[B,S], recon_reward[B,A], mu_all, log_var_all)``."""
+    ``(recon_state[B,S], recon_reward[B,A], mu_all, log_var_all)``.
+
+    ``emulate_bf16`` re-evaluates the same algorithm with the operand rounding points of the bf16 CUDA path.  With
+    ``fold`` (what the CUDA path does, csrc/fold.cu) two algebraically identical regroupings move rounding points:
+    encoder layer 0 is ``bf16(obs) . bf16(W0[:, I:])^T + (b0 + W0[:, :I] . emb)`` with the bracket in fp32, and layer 0 of
+    each decoder is ``bf16(z) . bf16(W0[:, :A L])^T + sum_a T_a[:, act_a] + b`` with ``T_a = bf16(W0[:, cols_a] . table_a^T)``.
+    In fp32 (``emulate_bf16=False``) the regrouping is invisible at 1e-5 and the reference's literal form is evaluated."""
     q = emulate_bf16
     L = spec.latent
+    A = spec.n_agents
     n_enc = len(spec.enc_hidden) + 1
     n_dec = len(spec.dec_hidden) + 1
-    zs, embs, mus, lvs = [], [], [], []
-    for a in idx_state.keys():
+    I = spec.idx_features
+    zs, embs, mus, lvs, act_idx = [], [], [], [], []
+    for k_a, a in enumerate(idx_state.keys()):
         x = idx_state[a].to(P["idx_emb.weight"].dtype)
         ids = x[:, 0].to(torch.int32).long()                     # model.py:142  .int()
-        h = _q(torch.cat([torch.nn.functional.embedding(ids, P["idx_emb.weight"]), x[:, 1:]], dim=1), q)
-        lat = _mlp(P, f"encoders.{a}", n_enc, h, q)
+        e_id = torch.nn.functional.embedding(ids, P["idx_emb.weight"])
+        codebook = bool((ids == k_a).all())                       # create_dataset's index column (trainer.py:21)
+        if q and fold and codebook:
+            W0, b0 = P[f"encoders.{a}.net.0.weight"], P[f"encoders.{a}.net.0.bias"]
+            first = torch.nn.functional.linear(_q(x[:, 1:], q), _q(W0[:, I:], q, True, False)) + (e_id @ W0[:, :I].t() + b0)
+            lat = _mlp(P, f"encoders.{a}", n_enc, None, q, first=first)
+        else:
+            h = _q(torch.cat([e_id, x[:, 1:]], dim=1), q)
+            lat = _mlp(P, f"encoders.{a}", n_enc, h, q)
         mu, lv = lat[:, :L], lat[:, L:]                           # model.py:149-150
         z = mu + eps[a].to(mu.dtype) * torch.exp(0.5 * lv)        # model.py:77-81
         if spec.discrete_act:
             ai = actions[a].to(torch.int32).long().reshape(-1)    # model.py:146
+            act_idx.append(ai)
             embs.append(torch.nn.functional.embedding(ai, P[f"action_encoder.{a}.weight"]))
         else:                                                     # model.py:148: ActionEncoder MLP on the raw action vector
             embs.append(_mlp(P, f"action_encoder.{a}", len(spec.act_hidden) + 1, _q(actions[a].to(mu.dtype), q), q))
         zs.append(z); mus.append(mu); lvs.append(lv)
-    dec_in = _q(torch.cat(zs + embs, dim=-1), q)                   # model.py:158-164: all z, then all act-emb
-    recon_s = _mlp(P, "state_decoder", n_dec, dec_in, q)
-    r = _mlp(P, "reward_decoder", n_dec, dec_in, q, out_fwd=True)
+    if q and fold and spec.discrete_act:
+        z_all = _q(torch.cat(zs, dim=-1), q)
+        Kz, C = A * L, spec.act_features
+
+        def layer0(prefix):
+            W0, b0 = P[f"{prefix}.net.0.weight"], P[f"{prefix}.net.0.bias"]
+            out = torch.nn.functional.linear(z_all, _q(W0[:, :Kz], q, True, False), b0)
+            for i, a in enumerate(idx_state.keys()):
+                T = _q(W0[:, Kz + i * C:Kz + (i + 1) * C] @ P[f"action_encoder.{a}.weight"].t(), q, True, False)   # [H, n_act]
+                out = out + T.t()[act_idx[i]]
+            return out
+        recon_s = _mlp(P, "state_decoder", n_dec, None, q, first=layer0("state_decoder"))
+        r = _mlp(P, "reward_decoder", n_dec, None, q, out_fwd=True, first=layer0("reward_decoder"))
+    else:
+        dec_in = _q(torch.cat(zs + embs, dim=-1), q)               # model.py:158-164: all z, then all act-emb
+        recon_s = _mlp(P, "state_decoder", n_dec, dec_in, q)
+        r = _mlp(P, "reward_decoder", n_dec, dec_in, q, out_fwd=True)
     recon_r = _q(torch.nn.functional.linear(r, _q(P["reward_linear.weight"], q, True, False), P["reward_linear.bias"]),
                  q, False, True)
     return recon_s, recon_r, mus, lvs

@@ -41,6 +41,25 @@ def digest_err(got, want):
     return max(abs(got[1] - want[1]) / l2, float(np.abs(got[2:] - want[2:]).max() / scale))
 
 
+def fp64_metrics(out, P, spec, idx_state, acts, eps, nxt, rew, huber, G32, mine_grads):
+    """fp32 is not exact: a ReLU unit whose pre-activation lies within round-off of zero takes either branch, and one such
+    unit moves a whole gradient row.  The yardstick for an fp32 implementation is therefore the exact (fp64) evaluation,
+    with the fp32 ORACLE's own distance from it as the scale of what fp32 can deliver at this shape."""
+    P64 = {k: v.double() for k, v in P.items()}
+    _, G64, _ = O.grads(P64, spec, {a: t.double() for a, t in idx_state.items()}, acts, {a: t.double() for a, t in eps.items()},
+                        nxt.double(), rew.double(), huber)
+    keys = sorted(mine_grads)
+
+    def cat(G):
+        return torch.cat([G[k].detach().double().cpu().reshape(-1) for k in keys])
+    ref = cat(G64)
+    out["whole_grad_rel_vs_fp64"] = float((cat(mine_grads) - ref).norm() / ref.norm())
+    out["oracle32_whole_grad_rel_vs_fp64"] = float((cat(G32) - ref).norm() / ref.norm())
+    out["grad_rel_max_vs_fp64"] = max(rel_l2(mine_grads[k], G64[k]) for k in keys)
+    out["oracle32_grad_rel_max_vs_fp64"] = max(rel_l2(G32[k], G64[k]) for k in keys)
+    out["grad_rel_median_vs_fp64"] = float(np.median([rel_l2(mine_grads[k], G64[k]) for k in keys]))
+
+
 def whole_grad(mine, ref):
     """relative L2 and cosine of the CONCATENATED gradient (every tensor that takes part) against `ref`."""
     a = torch.cat([p.grad.detach().double().cpu().reshape(-1) for _, p in sorted(mine.items())])
@@ -116,6 +135,7 @@ def main(case, precision, engine, mode="dropin", rng="eps", fusion="auto", flags
             Gq = None
             if step == 0 and precision == "bf16":      # gradients of the fused step against the bf16-emulating oracle
                 _, Gq, _ = O.grads(st.P, spec, idx_state, acts, eps, nxt, rew, huber, emulate_bf16=True)
+            P0 = {k: v.clone() for k, v in st.P.items()}
             losses_dev = m.train_step(pb, lr)
             sched.step()
             got_losses = [float(x) for x in losses_dev.cpu()]
@@ -135,8 +155,11 @@ def main(case, precision, engine, mode="dropin", rng="eps", fusion="auto", flags
                 gerr = {k: rel_l2(v, G[k]) for k, v in g_snap.items()}
                 out["grad_rel_max"] = max(gerr.values()); out["grad_rel_worst"] = max(gerr, key=gerr.get)
                 out["grad_rel_median"] = float(np.median(list(gerr.values())))
+                if not golden and precision == "fp32":
+                    fp64_metrics(out, P0, spec, idx_state, acts, eps, nxt, rew, huber, G, g_snap)
         else:
             got_losses = [float(loss), float(sl), float(rl), float(kl)]
+            P0 = st.P
             # oracle on the same inputs, same current parameters
             if mode == "jointmse":
                 jl, G, outs = oracle_joint_mse(st.P, spec, idx_state, acts, eps, joint)
@@ -163,6 +186,8 @@ def main(case, precision, engine, mode="dropin", rng="eps", fusion="auto", flags
                     if golden and mode != "jointmse":
                         gold[k] = digest_err(digest(p.grad, "grad." + k), rec["grad." + k])
                 out["whole_grad_rel"], out["whole_grad_cos"] = whole_grad(mine, G)
+                if not golden and precision == "fp32" and mode != "jointmse":
+                    fp64_metrics(out, P0, spec, idx_state, acts, eps, nxt, rew, huber, G, {k: p.grad for k, p in mine.items()})
                 out["grad_rel_top"] = sorted(((round(v, 6), k) for k, v in gerr.items()), reverse=True)[:10]
                 worst = max(gerr, key=gerr.get)
                 out["grad_rel_max"] = gerr[worst]; out["grad_rel_worst"] = worst
@@ -208,6 +233,9 @@ def main(case, precision, engine, mode="dropin", rng="eps", fusion="auto", flags
     perr = {k: rel_l2(p, st.P[k]) for k, p in mine.items()}
     pw = max(perr, key=perr.get)
     out["param3_rel_max"] = perr[pw]; out["param3_worst"] = pw
+    pa = torch.cat([p.detach().double().cpu().reshape(-1) for _, p in sorted(mine.items())])
+    pb_ = torch.cat([st.P[k].double().reshape(-1) for k, _ in sorted(mine.items())])
+    out["param3_whole_rel"] = float((pa - pb_).norm() / pb_.norm())
     if golden and mode != "jointmse" and not optenc:
         out["golden_param3_err"] = max(digest_err(digest(p, "param3." + k), rec["param3." + k]) for k, p in mine.items())
     print("STEP_CHECK " + json.dumps(out), flush=True)

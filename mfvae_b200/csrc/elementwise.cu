@@ -363,10 +363,64 @@ __global__ void __launch_bounds__(kThreads) recon_loss_kernel(ReconLossArgs p) {
   finish_scalar(tot, p.scratch, p.loss_scale, p.loss_out, red);
 }
 
+// Same pass, with the column sums of the gradient (= the bias gradient of the layer that produced `recon`) accumulated on the
+// way: a thread owns one 4-column strip and walks rows (blockIdx.y, += gridDim.y), so its column sums stay in registers and
+// leave with one fp32 atomic per column per CTA row-chunk.  The value summed is the STORED gradient (bf16-rounded when the
+// gradient buffer is bf16), exactly what the separate column-sum kernel read back from HBM.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) recon_loss_colsum_kernel(ReconLossArgs p) {
+  __shared__ float red[32];
+  T* grad = static_cast<T*>(p.grad);
+  const int wq = p.width / 4;
+  const int cq = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc = 0.f;
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cq < wq) {
+    const int c = cq * 4;
+    constexpr int U = 4;
+    for (int64_t b0 = blockIdx.y; b0 < p.B; b0 += static_cast<int64_t>(gridDim.y) * U) {
+      float4 r[U], t[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t b = min(b0 + static_cast<int64_t>(u) * gridDim.y, p.B - 1);      // clamped rows are loaded twice, used once
+        r[u] = p.recon16 ? load4<__nv_bfloat16>(p.recon16 + b * p.grad_ld + c) : ldg_stream4(p.recon + b * p.recon_ld + c);
+        t[u] = p.target16 ? load4<__nv_bfloat16>(p.target16 + b * p.target_ld + c) : ldg_stream4(p.target + b * p.target_ld + c);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t b = b0 + static_cast<int64_t>(u) * gridDim.y;
+        if (b >= p.B) break;
+        float4 g; float v0, v1, v2, v3;
+        recon_elem(r[u].x, t[u].x, p.huber, p.grad_scale, v0, g.x);
+        recon_elem(r[u].y, t[u].y, p.huber, p.grad_scale, v1, g.y);
+        recon_elem(r[u].z, t[u].z, p.huber, p.grad_scale, v2, g.z);
+        recon_elem(r[u].w, t[u].w, p.huber, p.grad_scale, v3, g.w);
+        acc += (v0 + v1) + (v2 + v3);
+        store4<T>(grad + b * p.grad_ld + c, g);
+        cs.x += to_f<T>(from_f<T>(g.x)); cs.y += to_f<T>(from_f<T>(g.y)); cs.z += to_f<T>(from_f<T>(g.z)); cs.w += to_f<T>(from_f<T>(g.w));
+      }
+    }
+    float* o = p.colsum_out + c;
+    atomicAdd(o, cs.x); atomicAdd(o + 1, cs.y); atomicAdd(o + 2, cs.z); atomicAdd(o + 3, cs.w);
+  }
+  const float tot = block_sum(acc, red);
+  finish_scalar(tot, p.scratch, p.loss_scale, p.loss_out, red);
+}
+
 int launch_recon_loss(const ReconLossArgs& a, cudaStream_t s) {
   const bool vec = a.width % 4 == 0 && (a.recon16 || a.recon_ld % 4 == 0) && a.target_ld % 4 == 0 && a.grad_ld % 4 == 0 &&
                    (reinterpret_cast<uintptr_t>(a.recon16 ? static_cast<const void*>(a.recon16) : static_cast<const void*>(a.recon)) % 16 == 0) && (reinterpret_cast<uintptr_t>(a.target16 ? static_cast<const void*>(a.target16) : static_cast<const void*>(a.target)) % 16 == 0) &&
                    (reinterpret_cast<uintptr_t>(a.grad) % 16 == 0);
+  if (a.colsum_out && vec && a.grad) {
+    const int wq = a.width / 4;
+    dim3 grid((wq + kThreads - 1) / kThreads, 1);
+    grid.y = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((a.B + 3) / 4, (kNumSMs * 8 + grid.x - 1) / grid.x)));
+    MFVAE_CHECK(static_cast<int64_t>(grid.x) * grid.y <= kMaxPartials, "recon loss: too many CTAs for the partial buffer");
+    if (a.grad_dtype == kBF16) recon_loss_colsum_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(a);
+    else                       recon_loss_colsum_kernel<float><<<grid, kThreads, 0, s>>>(a);
+    MFVAE_LAUNCH_CHECK();
+    return 0;
+  }
   const int64_t items = vec ? a.B * (a.width / 4) : a.B * a.width;
   const int grid = grid_for(items);
   if (a.grad_dtype == kBF16) {
@@ -377,6 +431,8 @@ int launch_recon_loss(const ReconLossArgs& a, cudaStream_t s) {
     else     recon_loss_kernel<float, false><<<grid, kThreads, 0, s>>>(a);
   }
   MFVAE_LAUNCH_CHECK();
+  // ragged widths / unaligned pointers: the column sum runs as its own pass
+  if (a.colsum_out && a.grad) return launch_colsum(a.grad, a.grad_dtype, 1, a.B, a.width, a.grad_ld, 0, a.colsum_out, 0, s);
   return 0;
 }
 

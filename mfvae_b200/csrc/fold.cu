@@ -51,36 +51,61 @@ int launch_onehot(const float* act, int act_ld, const int32_t* n_act, void* zin,
   return 0;
 }
 
-// T[h][a*nmax + k] = sum_c W0[h][wcol0 + a*C + c] * table[a][k][c]     one warp per (h, a); columns >= A*nmax are zeroed
+// T[h][a*nmax + k] = sum_c W0[h][wcol0 + a*C + c] * table[a][k][c]; columns >= A*nmax are zeroed.
+// One CTA per kRowsF rows of W0: the rows' action columns go through shared memory (coalesced 16-byte loads), thread j owns
+// output column j = a*nmax + k and reads its table row through the read-only cache (the whole table is A*nmax*C floats).
+constexpr int kRowsF = 4;
 template <typename T>
 __global__ void __launch_bounds__(kFoldThreads) act_fold_fwd_kernel(const float* __restrict__ W0, int64_t w_ld, int wcol0,
                                                                     const float* __restrict__ table, int64_t table_gs,
                                                                     T* __restrict__ Tt, int64_t t_ld, int rows, int A, int C, int nmax) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  const int64_t total = static_cast<int64_t>(rows) * A;
-  for (int64_t u = warp; u < total; u += nwarps) {
-    const int a = static_cast<int>(u % A);
-    const int64_t h = u / A;
-    const float* w = W0 + h * w_ld + wcol0 + a * C;
-    const float* tb = table + a * table_gs;
-    for (int k = 0; k < nmax; ++k) {
-      float acc = 0.f;
-      for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(w + c), __ldg(tb + static_cast<int64_t>(k) * C + c), acc);
-      acc = warp_sum(acc);
-      if (lane == 0) Tt[h * t_ld + a * nmax + k] = from_f<T>(acc);
+  extern __shared__ float wrow[];                      // [kRowsF][A*C]
+  const int AC = A * C;
+  const int h0 = blockIdx.x * kRowsF;
+  for (int i = threadIdx.x; i < kRowsF * (AC / 4); i += blockDim.x) {
+    const int r = i / (AC / 4), q = i - r * (AC / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (h0 + r < rows) v = ldg_stream4(W0 + static_cast<int64_t>(h0 + r) * w_ld + wcol0 + q * 4);
+    reinterpret_cast<float4*>(wrow)[i] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < t_ld; j += blockDim.x) {
+    float acc[kRowsF];
+#pragma unroll
+    for (int r = 0; r < kRowsF; ++r) acc[r] = 0.f;
+    if (j < A * nmax) {
+      const int a = j / nmax, k = j - a * nmax;
+      const float4* tb = reinterpret_cast<const float4*>(table + a * table_gs + static_cast<int64_t>(k) * C);
+      for (int c4 = 0; c4 < C / 4; ++c4) {
+        const float4 t = __ldg(tb + c4);
+#pragma unroll
+        for (int r = 0; r < kRowsF; ++r) {
+          const float4 w = reinterpret_cast<const float4*>(wrow + r * AC + a * C)[c4];
+          acc[r] = fmaf(w.x, t.x, fmaf(w.y, t.y, fmaf(w.z, t.z, fmaf(w.w, t.w, acc[r]))));
+        }
+      }
     }
-    if (a == A - 1) for (int j = A * nmax + lane; j < t_ld; j += 32) Tt[h * t_ld + j] = from_f<T>(0.f);
+#pragma unroll
+    for (int r = 0; r < kRowsF; ++r)
+      if (h0 + r < rows) Tt[static_cast<int64_t>(h0 + r) * t_ld + j] = from_f<T>(acc[r]);
   }
 }
 
 int launch_act_fold_fwd(const float* W0, int64_t w_ld, int wcol0, const float* table, int64_t table_gs, void* Tt, int dtype, int64_t t_ld,
                         int rows, int A, int C, int nmax, cudaStream_t s) {
-  const int64_t warps = static_cast<int64_t>(rows) * A;
-  const int grid = static_cast<int>(std::min<int64_t>((warps * 32 + kFoldThreads - 1) / kFoldThreads, kNumSMs * 8));
-  if (dtype == kBF16) act_fold_fwd_kernel<__nv_bfloat16><<<grid, kFoldThreads, 0, s>>>(W0, w_ld, wcol0, table, table_gs, static_cast<__nv_bfloat16*>(Tt), t_ld, rows, A, C, nmax);
-  else                act_fold_fwd_kernel<float><<<grid, kFoldThreads, 0, s>>>(W0, w_ld, wcol0, table, table_gs, static_cast<float*>(Tt), t_ld, rows, A, C, nmax);
+  MFVAE_CHECK(C % 4 == 0 && w_ld % 4 == 0 && wcol0 % 4 == 0 && table_gs % 4 == 0, "act fold: widths must be multiples of 4");
+  const size_t smem = static_cast<size_t>(kRowsF) * A * C * sizeof(float);
+  MFVAE_CHECK(smem <= 160 * 1024, "act fold: A * act_features too large for the shared-memory row buffer");
+  const int grid = (rows + kRowsF - 1) / kRowsF;
+  if (dtype == kBF16) {
+    static bool set16 = false;
+    if (!set16) { MFVAE_CUDA(cudaFuncSetAttribute(act_fold_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set16 = true; }
+    act_fold_fwd_kernel<__nv_bfloat16><<<grid, kFoldThreads, smem, s>>>(W0, w_ld, wcol0, table, table_gs, static_cast<__nv_bfloat16*>(Tt), t_ld, rows, A, C, nmax);
+  } else {
+    static bool set32 = false;
+    if (!set32) { MFVAE_CUDA(cudaFuncSetAttribute(act_fold_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set32 = true; }
+    act_fold_fwd_kernel<float><<<grid, kFoldThreads, smem, s>>>(W0, w_ld, wcol0, table, table_gs, static_cast<float*>(Tt), t_ld, rows, A, C, nmax);
+  }
   MFVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -88,53 +113,63 @@ int launch_act_fold_fwd(const float* W0, int64_t w_ld, int wcol0, const float* t
 // From dT [rows][t_ld] (fp32, complete):
 //   gW0[h][wcol0 + a*C + c]  = sum_k dT[h][a*nmax + k] * table[a][k][c]        (plain store: these columns have no other writer)
 //   gtable[a][k][c]         += sum_h dT[h][a*nmax + k] * W0[h][wcol0 + a*C + c] (atomics into the zeroed gradient arena)
-// grid = (row chunks, A); block = (C columns) x (256 / C row phases).  NMAX = compile-time bound on n_act.
+// grid = (row chunks of kRowsB, A); a thread owns 4 consecutive columns c (16-byte accesses) and walks the chunk's rows.
+constexpr int kRowsB = 128;
 template <int NMAX>
 __global__ void __launch_bounds__(kFoldThreads) act_fold_bwd_kernel(const float* __restrict__ dT, int64_t t_ld, const float* __restrict__ W0,
                                                                     float* __restrict__ gW0, int64_t w_ld, int wcol0,
                                                                     const float* __restrict__ table, float* __restrict__ gtable, int64_t table_gs,
-                                                                    int rows, int C, int nmax, int rows_per_cta) {
-  __shared__ float fold[kFoldThreads];
+                                                                    int rows, int C, int nmax) {
+  __shared__ float4 fold[kFoldThreads];
   const int a = blockIdx.y;
-  const int c = threadIdx.x % C, rphase = threadIdx.x / C, nph = blockDim.x / C;
-  float tab[NMAX], acc[NMAX];
+  const int strips = C / 4;
+  const int strip = threadIdx.x % strips, rphase = threadIdx.x / strips, nph = blockDim.x / strips;
+  float4 tab[NMAX], acc[NMAX];
 #pragma unroll
-  for (int k = 0; k < NMAX; ++k) { tab[k] = (k < nmax) ? __ldg(table + a * table_gs + static_cast<int64_t>(k) * C + c) : 0.f; acc[k] = 0.f; }
-  const int h0 = blockIdx.x * rows_per_cta, h1 = min(rows, h0 + rows_per_cta);
+  for (int k = 0; k < NMAX; ++k) {
+    tab[k] = (k < nmax) ? __ldg(reinterpret_cast<const float4*>(table + a * table_gs + static_cast<int64_t>(k) * C) + strip) : make_float4(0.f, 0.f, 0.f, 0.f);
+    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int h0 = blockIdx.x * kRowsB, h1 = min(rows, h0 + kRowsB);
   if (rphase < nph) {
     for (int h = h0 + rphase; h < h1; h += nph) {
       const float* d = dT + static_cast<int64_t>(h) * t_ld + a * nmax;
-      const int64_t wi = static_cast<int64_t>(h) * w_ld + wcol0 + a * C + c;
-      const float w = __ldg(W0 + wi);
-      float o = 0.f;
+      const int64_t wi = static_cast<int64_t>(h) * w_ld + wcol0 + a * C + strip * 4;
+      const float4 w = ldg_stream4(W0 + wi);
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < NMAX; ++k) {
-        if (k < nmax) { const float dk = __ldg(d + k); o = fmaf(dk, tab[k], o); acc[k] = fmaf(dk, w, acc[k]); }
+        if (k < nmax) {
+          const float dk = __ldg(d + k);
+          o.x = fmaf(dk, tab[k].x, o.x); o.y = fmaf(dk, tab[k].y, o.y); o.z = fmaf(dk, tab[k].z, o.z); o.w = fmaf(dk, tab[k].w, o.w);
+          acc[k].x = fmaf(dk, w.x, acc[k].x); acc[k].y = fmaf(dk, w.y, acc[k].y); acc[k].z = fmaf(dk, w.z, acc[k].z); acc[k].w = fmaf(dk, w.w, acc[k].w);
+        }
       }
-      gW0[wi] = o;
+      *reinterpret_cast<float4*>(gW0 + wi) = o;
     }
   }
 #pragma unroll
   for (int k = 0; k < NMAX; ++k) {
     if (k >= nmax) break;
     __syncthreads();
-    fold[threadIdx.x] = (rphase < nph) ? acc[k] : 0.f;
+    fold[threadIdx.x] = (rphase < nph) ? acc[k] : make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     if (rphase == 0) {
-      float t = fold[c];
-      for (int r = 1; r < nph; ++r) t += fold[r * C + c];
-      atomicAdd(gtable + a * table_gs + static_cast<int64_t>(k) * C + c, t);
+      float4 t = fold[strip];
+      for (int r = 1; r < nph; ++r) { const float4 u = fold[r * strips + strip]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+      float* o = gtable + a * table_gs + static_cast<int64_t>(k) * C + strip * 4;
+      atomicAdd(o, t.x); atomicAdd(o + 1, t.y); atomicAdd(o + 2, t.z); atomicAdd(o + 3, t.w);
     }
   }
 }
 
 int launch_act_fold_bwd(const float* dT, int64_t t_ld, const float* W0, float* gW0, int64_t w_ld, int wcol0, const float* table, float* gtable,
                         int64_t table_gs, int rows, int A, int C, int nmax, cudaStream_t s) {
-  MFVAE_CHECK(C <= kFoldThreads && nmax <= 16, "act fold: act_features <= 256 and n_act <= 16");
-  const int rows_per_cta = 64;
-  dim3 grid((rows + rows_per_cta - 1) / rows_per_cta, A);
-  if (nmax <= 8) act_fold_bwd_kernel<8><<<grid, kFoldThreads, 0, s>>>(dT, t_ld, W0, gW0, w_ld, wcol0, table, gtable, table_gs, rows, C, nmax, rows_per_cta);
-  else           act_fold_bwd_kernel<16><<<grid, kFoldThreads, 0, s>>>(dT, t_ld, W0, gW0, w_ld, wcol0, table, gtable, table_gs, rows, C, nmax, rows_per_cta);
+  MFVAE_CHECK(C / 4 <= kFoldThreads && C % 4 == 0 && nmax <= 16 && w_ld % 4 == 0 && wcol0 % 4 == 0 && table_gs % 4 == 0,
+              "act fold: act_features % 4 == 0, <= 1024 and n_act <= 16");
+  dim3 grid((rows + kRowsB - 1) / kRowsB, A);
+  if (nmax <= 8) act_fold_bwd_kernel<8><<<grid, kFoldThreads, 0, s>>>(dT, t_ld, W0, gW0, w_ld, wcol0, table, gtable, table_gs, rows, C, nmax);
+  else           act_fold_bwd_kernel<16><<<grid, kFoldThreads, 0, s>>>(dT, t_ld, W0, gW0, w_ld, wcol0, table, gtable, table_gs, rows, C, nmax);
   MFVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -161,27 +196,40 @@ int launch_enc_bias_fold(const float* W0, int64_t w_ld, const float* b0, const f
   return 0;
 }
 
-// g_emb[a][i] += sum_n W0[a][n][i] * db0[a][n]        gW0[a][n][i] = db0[a][n] * emb[a][i]   (i < I)       one CTA per agent
+// g_emb[a][i] += sum_n W0[a][n][i] * db0[a][n]        gW0[a][n][i] = db0[a][n] * emb[a][i]   (i < I)
+// grid = (N / kEmbRows, A): a CTA covers kEmbRows weight rows n of one agent; threads = (I columns) x (row phases)
+constexpr int kEmbRows = 16;
 __global__ void __launch_bounds__(kFoldThreads) emb_grad_fold_kernel(const float* __restrict__ W0, float* __restrict__ gW0, int64_t w_ld,
                                                                      const float* __restrict__ db0, const float* __restrict__ emb,
                                                                      float* __restrict__ g_emb, int N, int I) {
-  const int a = blockIdx.x;
-  for (int i = threadIdx.x; i < I; i += blockDim.x) {
+  __shared__ float fold[kFoldThreads];
+  const int a = blockIdx.y;
+  const int i = threadIdx.x % I, rphase = threadIdx.x / I, nph = blockDim.x / I;
+  const int n0 = blockIdx.x * kEmbRows, n1 = min(N, n0 + kEmbRows);
+  float acc = 0.f;
+  if (rphase < nph) {
     const float e = emb[static_cast<int64_t>(a) * I + i];
-    float acc = 0.f;
-    for (int n = 0; n < N; ++n) {
+    for (int n = n0 + rphase; n < n1; n += nph) {
       const int64_t wi = (static_cast<int64_t>(a) * N + n) * w_ld + i;
       const float d = db0[a * N + n];
       acc = fmaf(__ldg(W0 + wi), d, acc);
       gW0[wi] = d * e;
     }
-    atomicAdd(g_emb + static_cast<int64_t>(a) * I + i, acc);
+  }
+  fold[threadIdx.x] = acc;
+  __syncthreads();
+  if (rphase == 0) {
+    float t = fold[i];
+    for (int r = 1; r < nph; ++r) t += fold[r * I + i];
+    atomicAdd(g_emb + static_cast<int64_t>(a) * I + i, t);
   }
 }
 
 int launch_emb_grad_fold(const float* W0, float* gW0, int64_t w_ld, const float* db0, const float* emb, float* g_emb, int A, int N, int I,
                          cudaStream_t s) {
-  emb_grad_fold_kernel<<<A, kFoldThreads, 0, s>>>(W0, gW0, w_ld, db0, emb, g_emb, N, I);
+  MFVAE_CHECK(I <= kFoldThreads, "emb fold: idx_features <= 256");
+  dim3 grid((N + kEmbRows - 1) / kEmbRows, A);
+  emb_grad_fold_kernel<<<grid, kFoldThreads, 0, s>>>(W0, gW0, w_ld, db0, emb, g_emb, N, I);
   MFVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -554,7 +554,7 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
     // K-long GEMMs are bound by operand traffic from L2 (a 128 x BN x 64 step moves (128 + BN) * 128 bytes for
     // 128 * BN * 128 flops): a narrower tile that fills more SMs loses more to bandwidth than the idle SMs cost.
     // Model: time ~ waves * BN / eff(BN), eff measured on this kernel (tile GEMM rate relative to BN = 256).
-    if (k_blocks > 16 && op.epi != kEpiAccum) {
+    if (k_blocks > 16) {
       const double eff[3] = {1.0, 0.65, 0.35};
       double best = 1e30;
       for (int i = 0; i < 3; ++i) {
@@ -578,7 +578,9 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
   if (op.epi == kEpiAccum) {
     const long long tiles = static_cast<long long>(op.G) * m_tiles * n_tiles;
     long long want = op.split_k > 1 ? op.split_k : 1;
-    want = std::max<long long>(want, (static_cast<long long>(kNumSMs) * pl->cps + tiles - 1) / tiles);
+    // whole multiples only: splitting 80 tiles in two gives 160 work items = two rounds of half tiles on 148 SMs, i.e. the
+    // time of one round of whole tiles plus the atomics
+    want = std::max<long long>(want, (static_cast<long long>(kNumSMs) * pl->cps) / tiles);
     splits = static_cast<int>(std::max<long long>(1, std::min<long long>(want, std::max(1, k_blocks / 4))));
   }
   const int kb_per_split = (k_blocks + splits - 1) / splits;

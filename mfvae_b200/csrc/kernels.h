@@ -62,6 +62,7 @@ struct ReconLossArgs {
   float loss_scale;      // 1 / count_global
   float* loss_out;       // [1]
   float* scratch;        // >= 4096 floats
+  float* colsum_out = nullptr;   // optional [width] fp32: += column sums of the stored gradient (the producing layer's bias gradient)
 };
 int launch_recon_loss(const ReconLossArgs& a, cudaStream_t s);
 

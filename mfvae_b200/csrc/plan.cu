@@ -93,6 +93,7 @@ struct MfvaeHandle_ {
   // third stream: the reward head (two tiny GEMM chains) and the action-embedding kernels run beside the big layers
   cudaStream_t aux = nullptr;
   bool grads_zeroed = false;                 // mfvae_fwd_bwd: the gradient arena was zeroed on csum beside the forward pass
+  bool sout_bias_done = false;               // the state head's bias gradient was accumulated by the loss kernel (mfvae_fwd_bwd)
   cudaEvent_t zero_ev = nullptr, zero_fork_ev = nullptr;
   cudaEvent_t loss_ev = nullptr;             // the four loss scalars are final (recorded at the end of the loss phase)
   cudaStream_t csum = nullptr;               // fourth stream: the bias column sums (HBM-bound) run beside the wgrad GEMMs
@@ -315,7 +316,7 @@ static int build_ops(MfvaeHandle_* h) {
     o.A = D; o.a_gs = d_gs; o.a_rs = 1; o.a_cs = d_ld;
     o.B = X; o.b_gs = x_gs; o.b_rs = 1; o.b_cs = x_ld;
     o.C = out; o.c_gs = gw_gs; o.c_ld = gw_ld; o.c_dtype = kF32;
-    o.epi = kEpiAccum; o.split_k = pick_split_k(G, Nout, Kin, B);
+    o.epi = kEpiAccum; o.split_k = h->use_tc ? 1 : pick_split_k(G, Nout, Kin, B);     // the tcgen05 planner sizes its own split-K
     return push(o);
   };
   auto wgrad = [&](int G, int Nout, int Kin, const void* D, int64_t d_gs, int64_t d_ld, const void* X, int64_t x_gs, int64_t x_ld,
@@ -610,7 +611,7 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
 }
 
 static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStream_t s, bool state_fused = false, bool recon16 = false,
-                   bool join_reward = false) {
+                   bool join_reward = false, bool fuse_bias = false) {
   MFVAE_TRY(check_ready(h, b));
   MFVAE_CHECK(loss_kind >= MFVAE_LOSS_DEFAULT && loss_kind <= MFVAE_LOSS_JOINT_MSE, "unknown loss kind");
   const int joint_mse = (loss_kind == MFVAE_LOSS_JOINT_MSE);
@@ -631,7 +632,16 @@ static int do_loss(MfvaeHandle_* h, const MfvaeBatch* b, int loss_kind, cudaStre
   const float sw = joint_mse ? 1.0f : h->s_weight;
   a.grad_scale = static_cast<float>(static_cast<double>(sw) / cs); a.loss_scale = static_cast<float>(1.0 / cs);
   a.loss_out = losses_ptr(h) + 1; a.scratch = scratch_ptr(h, 1);
+  h->sout_bias_done = false;
+  if (!state_fused && fuse_bias && h->grads_zeroed) {
+    // train step: the gradient arena is already being zeroed beside the forward pass, so the loss kernel can leave the state
+    // head's bias gradient (column sums of d recon_s) behind and backward skips that 46 MB re-read
+    MFVAE_CUDA(cudaStreamWaitEvent(s, h->zero_ev, 0));
+    a.colsum_out = h->ar.d_grad + h->sOutB.off;
+    h->sout_bias_done = true;
+  }
   if (!state_fused) MFVAE_TRY(launch_recon_loss(a, s));
+  a.colsum_out = nullptr;
   if (join_reward && use_aux(h)) MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join2_ev, 0));   // reward head (aux stream) is needed from here
   a.recon = reinterpret_cast<const float*>(h->ws + h->RR.off); a.recon_ld = h->RR.ld; a.recon16 = nullptr;
   a.target = b->d_rew; a.target_ld = h->A; a.target16 = nullptr;
@@ -718,7 +728,8 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
   // output layers
   MFVAE_TRY(run_gemm(h, h->g_sout_dg, s));
   MFVAE_TRY(run_gemm(h, h->g_sout_wg, w));
-  MFVAE_TRY(launch_colsum(ws + h->DRS.off, dt, 1, h->B, h->S, h->DRS.ld, 0, G + h->sOutB.off, 0, cs));
+  if (!h->sout_bias_done) MFVAE_TRY(launch_colsum(ws + h->DRS.off, dt, 1, h->B, h->S, h->DRS.ld, 0, G + h->sOutB.off, 0, cs));
+  h->sout_bias_done = false;
   if (auxo) {                                                   // D of the last hidden layer: state half (s) + reward half (aux)
     MFVAE_CUDA(cudaEventRecord(h->aux_join_ev, h->aux));
     MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join_ev, 0));
@@ -1035,7 +1046,7 @@ int mfvae_fwd_bwd(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* s
     h->grads_zeroed = true;
   }
   MFVAE_TRY(do_forward(h, b, out, s, fuse, r16, true));
-  MFVAE_TRY(do_loss(h, b, MFVAE_LOSS_DEFAULT, s, fuse, r16, true));
+  MFVAE_TRY(do_loss(h, b, MFVAE_LOSS_DEFAULT, s, fuse, r16, true, true));
   return do_backward(h, b, s);
 }
 

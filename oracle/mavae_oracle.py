@@ -233,7 +233,8 @@ def _mlp(P, prefix: str, n_layers: int, x: torch.Tensor, q: bool = False, out_fw
 
 
 def forward(P: Dict[str, torch.Tensor], spec: Spec, idx_state: Dict[str, torch.Tensor],
-            actions: Dict[str, torch.Tensor], eps: Dict[str, torch.Tensor], emulate_bf16: bool = False, fold: bool = True):
+            actions: Dict[str, torch.Tensor], eps: Dict[str, torch.Tensor], emulate_bf16: bool = False, fold: bool = True,
+            fold_idx: Optional[bool] = None):
     """``MAVAE.forward`` with the normal draw made explicit.  Returns
     ``(recon_state[B,S], recon_reward[B,A], mu_all, log_var_all)``.
 
@@ -241,8 +242,10 @@ def forward(P: Dict[str, torch.Tensor], spec: Spec, idx_state: Dict[str, torch.T
     ``fold`` (what the CUDA path does, csrc/fold.cu) two algebraically identical regroupings move rounding points:
     encoder layer 0 is ``bf16(obs) . bf16(W0[:, I:])^T + (b0 + W0[:, :I] . emb)`` with the bracket in fp32, and layer 0 of
     each decoder is ``bf16(z) . bf16(W0[:, :A L])^T + sum_a T_a[:, act_a] + b`` with ``T_a = bf16(W0[:, cols_a] . table_a^T)``.
-    In fp32 (``emulate_bf16=False``) the regrouping is invisible at 1e-5 and the reference's literal form is evaluated."""
+    In fp32 (``emulate_bf16=False``) the regrouping is invisible at 1e-5 and the reference's literal form is evaluated.
+    ``fold_idx`` (default = ``fold``) switches the encoder regrouping alone: the fused encoder kernel keeps those columns dense."""
     q = emulate_bf16
+    fold_idx = fold if fold_idx is None else fold_idx
     L = spec.latent
     A = spec.n_agents
     n_enc = len(spec.enc_hidden) + 1
@@ -254,7 +257,7 @@ def forward(P: Dict[str, torch.Tensor], spec: Spec, idx_state: Dict[str, torch.T
         ids = x[:, 0].to(torch.int32).long()                     # model.py:142  .int()
         e_id = torch.nn.functional.embedding(ids, P["idx_emb.weight"])
         codebook = bool((ids == k_a).all())                       # create_dataset's index column (trainer.py:21)
-        if q and fold and codebook:
+        if q and fold_idx and codebook:
             W0, b0 = P[f"encoders.{a}.net.0.weight"], P[f"encoders.{a}.net.0.bias"]
             first = torch.nn.functional.linear(_q(x[:, 1:], q), _q(W0[:, I:], q, True, False)) + (e_id @ W0[:, :I].t() + b0)
             lat = _mlp(P, f"encoders.{a}", n_enc, None, q, first=first)
@@ -357,11 +360,11 @@ class OracleState:
 
 
 def grads(P, spec, idx_state, actions, eps, s_hat, r_hat, huber=True,
-          kl_weight=KL_WEIGHT, r_weight=R_WEIGHT, emulate_bf16=False):
+          kl_weight=KL_WEIGHT, r_weight=R_WEIGHT, emulate_bf16=False, fold=True, fold_idx=None):
     """Forward + loss + autograd backward.  Returns (losses 4-tuple of floats, dict of grads for every
     tensor that took part, outputs)."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
-    rs, rr, mus, lvs = forward(leaves, spec, idx_state, actions, eps, emulate_bf16)
+    rs, rr, mus, lvs = forward(leaves, spec, idx_state, actions, eps, emulate_bf16, fold, fold_idx)
     loss, sl, rl, kl = loss_s_r(rs, rr, s_hat.to(rs.dtype), r_hat.to(rs.dtype), mus, lvs, huber, kl_weight, r_weight)
     loss.backward()
     G = {k: v.grad for k, v in leaves.items() if v.grad is not None}

@@ -58,7 +58,7 @@ def test_folded_column_blocks_match_dense_fp32(batch, extra):
     assert o["finite"]
     assert max(o["fwd_mu"], o["fwd_lv"], o["fwd_rs"], o["fwd_rr"]) < 1e-5, o
     assert max(o["loss_rel"]) < 1e-5, o
-    assert o["grad_rel_median"] < 1e-5 and o["whole_grad_rel"] < 1e-4, o
+    assert o["grad_rel_median"] < 1e-5 and o["whole_grad_rel"] < 5e-4, o
 
 
 def test_folded_column_blocks_match_dense_bf16():

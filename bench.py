@@ -502,6 +502,7 @@ def run_ours(args, w):
                 "e2e_fp32_rows": None if e2e_fp32 is None else {"value": e2e_fp32[0], "unit": UNIT, "h2d_bytes_per_step": e2e_fp32[1]},
                 "e2e_bf16_targets": None if e2e_t16 is None else {"value": e2e_t16[0], "unit": UNIT, "h2d_bytes_per_step": e2e_t16[1],
                                                                   "note": "next-observation targets also bf16 on the host: rounds the loss target (opt-in)"},
+                "comm": getattr(m, "comm_info", None),
                 "gpu_launches": int(launches), "clocks": clocks, "losses_last_step": loss_host,
                 "model_tflops": value * flops_per_sample(spec) / 1e12 / world,
                 "roofline": roof, "cpu_baseline": cpu, "eager_b200": eager}

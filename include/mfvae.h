@@ -176,6 +176,9 @@ int mfvae_adam_step_overlapped(MfvaeHandle h, float lr, float beta1, float beta2
 int mfvae_adam_range(MfvaeHandle h, int64_t begin, int64_t end, float lr, float beta1, float beta2, float eps, int64_t t,
                      void* stream);
 int mfvae_wait_decoder_reads(MfvaeHandle h, void* stream);
+/* finer guard: `stream` waits until backward has finished reading the weights of gradient bucket i (so that bucket's Adam
+ * can start while later layers are still in backward) */
+int mfvae_bucket_read_wait(MfvaeHandle h, int32_t i, void* stream);
 /* persistent GEMM grids use (148 - n_sms) SMs, leaving room for the collective's kernels that run beside backward: a
  * persistent kernel whose CTAs cannot all be resident at once runs a second wave (process-wide setting) */
 int mfvae_set_sm_reserve(MfvaeHandle h, int32_t n_sms);
@@ -202,6 +205,28 @@ int mfvae_bucket(MfvaeHandle h, int32_t i, int64_t* begin, int64_t* end, void** 
 int mfvae_loss_wait(MfvaeHandle h, void* stream);
 /* make `stream` (e.g. the NCCL stream) wait for bucket i's event */
 int mfvae_bucket_wait(MfvaeHandle h, int32_t i, void* stream);
+
+/* Data-parallel exchange step as the library's own kernels over NVLink / NVSwitch peer memory (csrc/comm.cu; SURVEY.md 8b asked
+ * for mfvae_allreduce_grads next to the NCCL route).  The host maps ONE symmetric buffer of mfvae_comm_window_bytes() bytes per
+ * rank into every rank (CUDA VMM / fabric handles; torch.distributed._symmetric_memory does it for the Python host) and hands in
+ *   d_peer_windows   device array [world] of the windows' base addresses as mapped in THIS process (own window included)
+ *   multicast_window multicast (NVLS) mapping of the same windows, or NULL -> plain peer loads / stores
+ *   d_signal_pads    device array [world] of zero-initialised 32-bit flag pads of signal_pad_bytes each (slots [0, 64) are not used)
+ * payload_bf16 = 1 ships gradients as bf16 (the switch / the reducing rank accumulates in fp32); 0 ships fp32.
+ * Every rank must issue the same sequence of mfvae_allreduce_* calls.  max_blocks (0 = 64) caps the CTAs of a reduce; one 32-bit
+ * flag per (CTA, peer) is used behind the first 64 slots of a pad, so signal_pad_bytes bounds it too. */
+int mfvae_comm_bind(MfvaeHandle h, int32_t rank, int32_t world, void* const* d_peer_windows, void* multicast_window,
+                    void* const* d_signal_pads, int64_t signal_pad_bytes, void* local_window, int64_t window_bytes, int32_t payload_bf16,
+                    int32_t max_blocks);
+int64_t mfvae_comm_window_bytes(MfvaeHandle h, int32_t payload_bf16);
+/* sum over ranks of gradient-arena elements [begin, end) (a bucket of mfvae_bucket), on `stream`; do_adam = 1 runs the fused
+ * Adam of that range right behind it (reduced gradient read from the window, fp32 copy left in the gradient arena) */
+int mfvae_allreduce_grads(MfvaeHandle h, int64_t begin, int64_t end, int32_t do_adam, float lr, float beta1, float beta2, float eps,
+                          int64_t t, void* stream);
+/* do_adam = 1 sweeps run on an internal optimizer stream behind their reduce; this makes `stream` wait for all of them */
+int mfvae_opt_join(MfvaeHandle h, void* stream);
+/* sum over ranks of the 4 loss scalars of the step in flight, in place */
+int mfvae_allreduce_losses(MfvaeHandle h, void* stream);
 
 /* standalone bandwidth-bound kernels (BASELINE config 5 microbenchmarks; also used by the step).
  * dtype: 0 = fp32 activations, 1 = bf16 activations (mu / logvar / recon / target stay fp32). */

@@ -80,6 +80,7 @@ SIGNATURES = {
     "mfvae_adam_step_overlapped": (C.c_int, [_vp, _f, _f, _f, _f, _i64, _vp]),
     "mfvae_adam_range": (C.c_int, [_vp, _i64, _i64, _f, _f, _f, _f, _i64, _vp]),
     "mfvae_wait_decoder_reads": (C.c_int, [_vp, _vp]),
+    "mfvae_bucket_read_wait": (C.c_int, [_vp, _i32, _vp]),
     "mfvae_set_sm_reserve": (C.c_int, [_vp, _i32]),
     "mfvae_fwd_bwd": (C.c_int, [_vp, C.POINTER(MfvaeBatch), C.POINTER(MfvaeOutputs), _vp]),
     "mfvae_launch_count": (C.c_uint64, []),
@@ -89,6 +90,11 @@ SIGNATURES = {
     "mfvae_bucket": (C.c_int, [_vp, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_vp)]),
     "mfvae_bucket_wait": (C.c_int, [_vp, _i32, _vp]),
     "mfvae_loss_wait": (C.c_int, [_vp, _vp]),
+    "mfvae_comm_bind": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32]),
+    "mfvae_opt_join": (C.c_int, [_vp, _vp]),
+    "mfvae_comm_window_bytes": (_i64, [_vp, _i32]),
+    "mfvae_allreduce_grads": (C.c_int, [_vp, _i64, _i64, _i32, _f, _f, _f, _f, _i64, _vp]),
+    "mfvae_allreduce_losses": (C.c_int, [_vp, _vp]),
     "mfvae_reparam_kl": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _u64, _u64, _i64, _i64, _vp, _vp, _vp]),
     "mfvae_recon_loss": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _f, _i64, _vp, _vp, _vp]),
     "mfvae_adam_flat": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i64, _vp]),

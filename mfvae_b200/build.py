@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmfvae_b200.so")
-SOURCES = ["elementwise.cu", "enc_fused.cu", "fold.cu", "gemm_simt.cu", "gemm_tc.cu", "plan.cu", "ring.cu"]
+SOURCES = ["comm.cu", "elementwise.cu", "enc_fused.cu", "fold.cu", "gemm_simt.cu", "gemm_tc.cu", "plan.cu", "ring.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

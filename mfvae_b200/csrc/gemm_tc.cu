@@ -543,7 +543,7 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
   const int m_tiles = (op.M + BM - 1) / BM;
   // tile width: the widest BN that still gives every SM a tile; otherwise the narrowest that covers N
   const int k_blocks = (op.K + BK - 1) / BK;
-  int BN = 64;
+  int BN = 64, forced_splits = 0;
   {
     const int cands[3] = {256, 128, 64};
     for (int c : cands) {
@@ -553,16 +553,26 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
     }
     // K-long GEMMs are bound by operand traffic from L2 (a 128 x BN x 64 step moves (128 + BN) * 128 bytes for
     // 128 * BN * 128 flops): a narrower tile that fills more SMs loses more to bandwidth than the idle SMs cost.
-    // Model: time ~ waves * BN / eff(BN), eff measured on this kernel (tile GEMM rate relative to BN = 256).
-    if (k_blocks > 16) {
-      const double eff[3] = {1.0, 0.65, 0.35};
+    // Model (microseconds): rounds over the 148 SMs x (k-blocks per work item x time of one 128 x BN x 64 step + epilogue),
+    // step times measured on this kernel: 0.57 / 0.44 / 0.41 us for BN = 256 / 128 / 64.  Single-matrix weight gradients also
+    // choose their split-K here: a work item is (tile, K range), items beyond one round cost a whole extra round, and a
+    // split epilogue pays fp32 atomics instead of plain stores.  (Grouped wgrads of the small layers keep the narrow shape.)
+    forced_splits = 0;
+    if (k_blocks > 16 && (op.epi != kEpiAccum || op.G == 1)) {
+      const double step_us[3] = {0.57, 0.44, 0.41};
       double best = 1e30;
       for (int i = 0; i < 3; ++i) {
         const int c = cands[i];
         if (c > 64 && c / 2 >= op.N) continue;
         const long long t = static_cast<long long>(op.G) * m_tiles * ((op.N + c - 1) / c);
-        const double cost = static_cast<double>((t + kNumSMs - 1) / kNumSMs) * c / eff[i];
-        if (cost < best) { best = cost; BN = c; }
+        const int max_s = (op.epi == kEpiAccum) ? std::max(1, std::min(16, k_blocks / 4)) : 1;
+        for (int sp = 1; sp <= max_s; ++sp) {
+          const int kbs = (k_blocks + sp - 1) / sp;
+          if (sp > 1 && (k_blocks + kbs - 1) / kbs != sp) continue;          // this split count leaves an empty split
+          const double epi = (c / 64) * (sp > 1 ? 2.0 : 1.0) + 2.0;
+          const double cost = static_cast<double>((t * sp + kNumSMs - 1) / kNumSMs) * (kbs * step_us[i] + epi) * (sp > 1 ? 1.1 : 1.0);   // near-ties keep plain stores
+          if (cost < best) { best = cost; BN = c; forced_splits = sp; }
+        }
       }
     }
   }
@@ -572,10 +582,12 @@ int gemm_tc_plan(const GemmOp& op, TcPlan** out) {
   //    kernels of the other backward chain (side stream) on the same SM, and 3 x 72 KB of operands in flight per SM
   //    covers the L2 latency-bandwidth product as well as one deep ring does.
   // (measured again with 256-wide tiles kept for K <= 256: enc layer 3 forward 37 -> 52 us, its dgrad 56 -> 69 us)
-  if (k_blocks <= 4 || BN == 64) { BN = 64; pl->cps = 3; }     // BN == 64 here: not even 128-wide tiles reach 148
+  if (k_blocks <= 4 || (BN == 64 && forced_splits == 0)) { BN = 64; pl->cps = 3; }     // BN == 64 here: not even 128-wide tiles reach 148
   const int n_tiles = (op.N + BN - 1) / BN;
   int splits = 1;
-  if (op.epi == kEpiAccum) {
+  if (op.epi == kEpiAccum && forced_splits > 0 && op.split_k <= 1) {
+    splits = forced_splits;
+  } else if (op.epi == kEpiAccum) {
     const long long tiles = static_cast<long long>(op.G) * m_tiles * n_tiles;
     long long want = op.split_k > 1 ? op.split_k : 1;
     // whole multiples only: splitting 80 tiles in two gives 160 work items = two rounds of half tiles on 148 SMs, i.e. the

@@ -94,6 +94,28 @@ int launch_philox_normal(float* out, int64_t B, int width, uint64_t seed, uint64
 int launch_loss_total(float* losses, float s_weight, float r_weight, float kl_weight, cudaStream_t s, const float* partials = nullptr,
                       int n_partials = 0, float partial_scale = 0.f);
 
+// ---- data-parallel exchange over peer memory (comm.cu) ------------------------------------------
+struct CommCtx {
+  int rank = 0, world = 1;
+  void* const* d_peers = nullptr;      // device array [world]: base pointer of every rank's window of the symmetric buffer
+  void* mc = nullptr;                  // multicast base of the windows (NVSwitch), or nullptr -> plain peer loads / stores
+  uint32_t* const* d_pads = nullptr;   // device array [world]: every rank's signal pad
+  void* local = nullptr;               // this rank's window
+  int dtype = kF32;                    // payload type of the gradient region (element i of the arena at element i of the window)
+  int64_t elems = 0;                   // gradient region: elements
+  int64_t scalar_off = 0;              // byte offset of a 256-byte fp32 scalar region behind it
+  int64_t small_off = 0, small_bytes = 0;   // fp32 scratch for tiny ranges reduced by one single-CTA kernel
+  int max_blocks = 16;
+};
+int comm_pack(const float* g, void* window, int dtype, int64_t begin, int64_t end, cudaStream_t s);
+int comm_unpack(const void* window, int dtype, float* g, int64_t begin, int64_t end, cudaStream_t s);
+int comm_allreduce(const CommCtx& c, int64_t begin, int64_t end, cudaStream_t s);
+int comm_allreduce_scalars(const CommCtx& c, const float* src, int n, float* out, cudaStream_t s);
+int comm_small_allreduce_adam(const CommCtx& c, int64_t n, float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, int do_adam,
+                              float lr, float b1, float b2, float eps, int64_t t, cudaStream_t s);
+int launch_adam_payload(float* p, const void* gw, int dtype, float* g, float* m, float* v, __nv_bfloat16* shadow, int64_t n,
+                        float lr, float b1, float b2, float eps, int64_t t, cudaStream_t s);
+
 // ---- folded constant-input column blocks (fold.cu) ---------------------------------------------
 int launch_onehot(const float* act, int act_ld, const int32_t* n_act, void* zin, int dtype, int64_t zin_ld, int col0, int A, int nmax,
                   int width, int64_t B, cudaStream_t s);

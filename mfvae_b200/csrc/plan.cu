@@ -101,12 +101,15 @@ struct MfvaeHandle_ {
   cudaEvent_t aux_fork_ev = nullptr, aux_join_ev = nullptr, aux_fork2_ev = nullptr, aux_join2_ev = nullptr;
   cudaStream_t opt_stream = nullptr;         // overlapped Adam
   cudaEvent_t opt_ev = nullptr, dec_read_ev = nullptr;
+  cudaEvent_t read_ev[3] = {nullptr, nullptr, nullptr};   // backward has finished READING the weights of gradient bucket 0 / 1 / 2
 
   // optional per-GEMM event timing (bench.py roofline)
   bool profiling = false;
   std::vector<cudaEvent_t> prof_ev;          // 2 per GEMM op
   std::vector<char> prof_hit;
 
+  std::vector<cudaEvent_t> ar_ev = std::vector<cudaEvent_t>(8, nullptr); size_t ar_ev_i = 0;   // reduce -> optimizer-stream hand-off
+  CommCtx comm;                              // data-parallel exchange over peer memory (mfvae_comm_bind); world == 1: unbound
   // gradient buckets (arena ranges) and their completion events
   struct Bucket { int64_t begin, end; cudaEvent_t ev; };
   std::vector<Bucket> buckets;
@@ -734,6 +737,7 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
     MFVAE_CUDA(cudaEventRecord(h->aux_join_ev, h->aux));
     MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join_ev, 0));
   }
+  MFVAE_CUDA(cudaEventRecord(h->read_ev[0], s));                // the three output-layer dgrads (readers of bucket 0's weights) are queued
   MFVAE_TRY(run_gemm(h, h->g_rl_wg, rw));
   MFVAE_TRY(launch_colsum(ws + h->DRR.off, dt, 1, h->B, A, h->DRR.ld, 0, G + h->rlb.off, 0, rw));
   if (!auxo) MFVAE_TRY(fork());                                 // D(reward decoder output) from the dgrad chain
@@ -761,11 +765,13 @@ static int do_backward(MfvaeHandle_* h, const MfvaeBatch* b, cudaStream_t s, con
     MFVAE_TRY(launch_colsum(ws + h->DHD[l].off, dt, 1, h->B, 2 * h->decH[l], h->DHD[l].ld, 0, G + h->decB[l].off, 0, cs));
     if (l == 1) { MFVAE_TRY(csum_into_w()); MFVAE_CUDA(cudaEventRecord(h->buckets[1].ev, w)); }
     MFVAE_TRY(run_gemm(h, h->g_dec_dg[l], s));
+    if (l == 1) MFVAE_CUDA(cudaEventRecord(h->read_ev[1], s));    // decoder layers >= 1 have been read
   }
-  if (nh == 1) MFVAE_CUDA(cudaEventRecord(h->buckets[1].ev, w));
+  if (nh == 1) { MFVAE_CUDA(cudaEventRecord(h->buckets[1].ev, w)); MFVAE_CUDA(cudaEventRecord(h->read_ev[1], s)); }
   MFVAE_TRY(csum_into_w());
   MFVAE_CUDA(cudaEventRecord(h->buckets[2].ev, w));
   if (h->dec_read_ev) MFVAE_CUDA(cudaEventRecord(h->dec_read_ev, s));   // last reader of the decoder weights (dgrad layer 0) is queued
+  MFVAE_CUDA(cudaEventRecord(h->read_ev[2], s));
   // action tables (model.py:121: unregistered; gradients still flow)
   cudaStream_t at = s;
   if (auxo) {
@@ -899,6 +905,7 @@ int mfvae_create(const MfvaeConfig* cfg, int device, MfvaeHandle* out) {
   if (cudaStreamCreateWithFlags(&h->opt_stream, cudaStreamNonBlocking) != cudaSuccess) h->opt_stream = nullptr;
   cudaEventCreateWithFlags(&h->opt_ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->dec_read_ev, cudaEventDisableTiming);
+  for (int i = 0; i < 3; ++i) cudaEventCreateWithFlags(&h->read_ev[i], cudaEventDisableTiming);
   std::vector<int32_t> meta;
   meta.insert(meta.end(), h->obs_off.begin(), h->obs_off.end());
   meta.insert(meta.end(), h->obs_dim.begin(), h->obs_dim.end());
@@ -928,8 +935,10 @@ int mfvae_destroy(MfvaeHandle h) {
   for (auto e : h->csum_ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {h->aux_fork_ev, h->aux_join_ev, h->aux_fork2_ev, h->aux_join2_ev}) if (e) cudaEventDestroy(e);
   if (h->eb_ev) cudaEventDestroy(h->eb_ev);
+  for (auto e : h->ar_ev) if (e) cudaEventDestroy(e);
   if (h->opt_ev) cudaEventDestroy(h->opt_ev);
   if (h->dec_read_ev) cudaEventDestroy(h->dec_read_ev);
+  for (int i = 0; i < 3; ++i) if (h->read_ev[i]) cudaEventDestroy(h->read_ev[i]);
   if (h->opt_stream) cudaStreamDestroy(h->opt_stream);
   if (h->d_meta) cudaFree(h->d_meta);
   delete h;
@@ -1071,9 +1080,14 @@ int mfvae_adam_step_overlapped(MfvaeHandle h, float lr, float beta1, float beta2
     return launch_adam(h->ar.d_param + b, h->ar.d_grad + b, h->ar.d_m + b, h->ar.d_v + b, sh ? sh + b : nullptr, e - b,
                        lr, beta1, beta2, eps, t, st, st == s ? 8 : 4);
   };
-  for (int i = 0; i < 3; ++i) MFVAE_CUDA(cudaStreamWaitEvent(h->opt_stream, h->buckets[i].ev, 0));
-  MFVAE_CUDA(cudaStreamWaitEvent(h->opt_stream, h->dec_read_ev, 0));    // the dgrad chain has finished reading the decoder weights
-  MFVAE_TRY(range(h->reg2_begin, h->enc_begin, h->opt_stream));
+  // one launch per gradient bucket, each as soon as that bucket's gradients are final AND backward no longer reads its weights:
+  // the output layers' 174 MB sweep runs beside the decoder's latency-bound middle, the decoder-layer-0 sweep beside the
+  // encoder half of backward, instead of one 523 MB sweep fighting the encoder wgrads for HBM at the end of the step
+  for (int i = 0; i < 3; ++i) {
+    MFVAE_CUDA(cudaStreamWaitEvent(h->opt_stream, h->buckets[i].ev, 0));
+    MFVAE_CUDA(cudaStreamWaitEvent(h->opt_stream, h->read_ev[i], 0));
+    MFVAE_TRY(range(h->buckets[i].begin, h->buckets[i].end, h->opt_stream));
+  }
   MFVAE_CUDA(cudaEventRecord(h->opt_ev, h->opt_stream));
   MFVAE_TRY(range(0, h->reg2_begin, s));
   if (h->optimized_elems > h->enc_begin) MFVAE_TRY(range(h->enc_begin, h->optimized_elems, s));
@@ -1091,6 +1105,13 @@ int mfvae_adam_range(MfvaeHandle h, int64_t begin, int64_t end, float lr, float 
   return launch_adam(h->ar.d_param + begin, h->ar.d_grad + begin, h->ar.d_m + begin, h->ar.d_v + begin, sh ? sh + begin : nullptr,
                      end - begin, lr, beta1, beta2, eps, t, static_cast<cudaStream_t>(stream));
 }
+// make `stream` wait until the backward pass in flight has finished READING the weights gradient bucket i covers (buckets
+// 0..2: output layers, decoder layers >= 1, decoder layer 0; later buckets have no reader left once their event has fired)
+int mfvae_bucket_read_wait(MfvaeHandle h, int32_t i, void* stream) {
+  MFVAE_CHECK(h && i >= 0 && i < static_cast<int32_t>(h->buckets.size()), "bucket index out of range");
+  if (i < 3 && h->read_ev[i]) MFVAE_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->read_ev[i], 0));
+  return 0;
+}
 // make `stream` wait until the backward pass in flight has finished READING the decoder / output-layer weights
 int mfvae_wait_decoder_reads(MfvaeHandle h, void* stream) {
   MFVAE_CHECK(h && h->dec_read_ev, "no backward pass has been recorded");
@@ -1105,6 +1126,83 @@ int mfvae_set_sm_reserve(MfvaeHandle h, int32_t n_sms) {
   g_tc_sm_reserve = n_sms;
   if (h && h->ws && h->ar.d_param) return build_ops(h);
   return 0;
+}
+
+// ---- data-parallel exchange over peer memory (comm.cu) ----
+constexpr int64_t kCommSmallBytes = 64 * 1024;      // ranges up to 16 K elements take the single-kernel path
+int mfvae_comm_bind(MfvaeHandle h, int32_t rank, int32_t world, void* const* d_peer_windows, void* multicast_window,
+                    void* const* d_signal_pads, int64_t signal_pad_bytes, void* local_window, int64_t window_bytes, int32_t payload_bf16,
+                    int32_t max_blocks) {
+  MFVAE_CHECK(h && h->device >= 0, "comm: needs a device handle");
+  MFVAE_CHECK(world >= 2 && world <= 16 && rank >= 0 && rank < world, "comm: bad rank / world");
+  MFVAE_CHECK(d_peer_windows && d_signal_pads && local_window, "comm: null window / pad pointers");
+  MFVAE_CHECK(reinterpret_cast<uintptr_t>(local_window) % 256 == 0, "comm: the window must be 256-byte aligned");
+  const int64_t es = payload_bf16 ? 2 : 4;
+  const int64_t elems = round_up(h->optimized_elems, 8);
+  const int64_t scalar_off = round_up(elems * es, 256);
+  MFVAE_CHECK(window_bytes >= scalar_off + 256 + kCommSmallBytes, "comm: window too small (mfvae_comm_window_bytes)");
+  CommCtx& c = h->comm;
+  c.rank = rank; c.world = world; c.d_peers = d_peer_windows; c.mc = multicast_window;
+  c.d_pads = reinterpret_cast<uint32_t* const*>(d_signal_pads); c.local = local_window;
+  c.dtype = payload_bf16 ? kBF16 : kF32; c.elems = elems; c.scalar_off = scalar_off;
+  c.small_off = scalar_off + 256; c.small_bytes = kCommSmallBytes;
+  // one 32-bit flag per (block, peer) behind the 64 slots left to the host framework
+  const int64_t slot_blocks = (signal_pad_bytes / 4 - 64) / world;
+  MFVAE_CHECK(slot_blocks >= 1, "comm: signal pads too small (need >= 256 + 4 * world bytes)");
+  c.max_blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(max_blocks > 0 ? max_blocks : 64, slot_blocks), kNumSMs)));
+  for (auto& e : h->ar_ev) if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  return 0;
+}
+int64_t mfvae_comm_window_bytes(MfvaeHandle h, int32_t payload_bf16) {
+  if (!h) return -1;
+  return round_up(round_up(h->optimized_elems, 8) * (payload_bf16 ? 2 : 4), 256) + 256 + kCommSmallBytes;
+}
+// all-reduce (sum) of the gradient arena's elements [begin, end) across ranks, on `stream`: pack -> two-shot reduce in the
+// windows.  With do_adam the fused Adam of that range follows (reading the reduced gradient from the window and leaving its
+// fp32 copy in the gradient arena); without, the reduced gradient is unpacked into the gradient arena.
+int mfvae_allreduce_grads(MfvaeHandle h, int64_t begin, int64_t end, int32_t do_adam, float lr, float beta1, float beta2, float eps,
+                          int64_t t, void* stream) {
+  MFVAE_CHECK(h && h->comm.world >= 2, "comm: mfvae_comm_bind has not been called");
+  MFVAE_CHECK(begin >= 0 && end <= h->comm.elems && begin % 8 == 0, "comm: range outside the optimised prefix or not 8-element aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t e8 = round_up(end, 8);
+  if (e8 <= begin) return 0;
+  const CommCtx& c = h->comm;
+  if ((e8 - begin) * 4 <= c.small_bytes) {
+    __nv_bfloat16* sh = static_cast<__nv_bfloat16*>(h->ar.d_shadow_bf16);
+    return comm_small_allreduce_adam(c, e8 - begin, h->ar.d_param + begin, h->ar.d_grad + begin, h->ar.d_m + begin, h->ar.d_v + begin,
+                                     sh ? sh + begin : nullptr, do_adam, lr, beta1, beta2, eps, t, s);
+  }
+  MFVAE_TRY(comm_pack(h->ar.d_grad, c.local, c.dtype, begin, e8, s));
+  MFVAE_TRY(comm_allreduce(c, begin, e8, s));
+  if (do_adam) {
+    // the optimizer sweep of this range runs on the handle's optimizer stream behind the reduce, so that the next bucket's
+    // reduce (on `stream`) does not queue behind a 100-200 MB sweep; mfvae_opt_join makes the caller's stream wait for it
+    const int64_t es = (c.dtype == kBF16) ? 2 : 4;
+    __nv_bfloat16* sh = static_cast<__nv_bfloat16*>(h->ar.d_shadow_bf16);
+    cudaStream_t o = h->opt_stream ? h->opt_stream : s;
+    if (o != s) {
+      cudaEvent_t ev = h->ar_ev[h->ar_ev_i++ % h->ar_ev.size()];
+      MFVAE_CUDA(cudaEventRecord(ev, s));
+      MFVAE_CUDA(cudaStreamWaitEvent(o, ev, 0));
+    }
+    MFVAE_TRY(launch_adam_payload(h->ar.d_param + begin, static_cast<const char*>(c.local) + begin * es, c.dtype, h->ar.d_grad + begin,
+                                  h->ar.d_m + begin, h->ar.d_v + begin, sh ? sh + begin : nullptr, e8 - begin, lr, beta1, beta2, eps, t, o));
+    if (o != s) MFVAE_CUDA(cudaEventRecord(h->opt_ev, o));
+    return 0;
+  }
+  return comm_unpack(c.local, c.dtype, h->ar.d_grad, begin, e8, s);
+}
+// make `stream` wait for every optimizer sweep issued by mfvae_allreduce_grads(do_adam = 1) so far
+int mfvae_opt_join(MfvaeHandle h, void* stream) {
+  MFVAE_CHECK(h, "null handle");
+  if (h->opt_stream && h->opt_ev) MFVAE_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->opt_ev, 0));
+  return 0;
+}
+// sum of the 4 loss scalars of the step in flight across ranks (in place in the handle's loss slots), on `stream`
+int mfvae_allreduce_losses(MfvaeHandle h, void* stream) {
+  MFVAE_CHECK(h && h->comm.world >= 2 && h->ws, "comm: not bound");
+  return comm_allreduce_scalars(h->comm, losses_ptr(h), 4, losses_ptr(h), static_cast<cudaStream_t>(stream));
 }
 
 uint64_t mfvae_launch_count(void) { return g_launch_count; }

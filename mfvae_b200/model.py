@@ -313,6 +313,8 @@ class MAVAE(nn.Module):
         self._cb = None
         self._last_mu = self._last_lv = None
         self._comm_stream = None
+        self._native_comm = False
+        self.comm_info = {"route": "none"}
 
     # ------------------------------------------------------------------ construction helpers
     def _view(self, info, arena):
@@ -689,6 +691,38 @@ class MAVAE(nn.Module):
         return dist.get_world_size(self._pg)
 
     # ---- data parallel: bucketed all-reduce on a side stream, launched as each bucket's event fires ----
+    def _bind_native_comm(self, process_group):
+        """The exchange step as the library's own kernels (csrc/comm.cu): one symmetric buffer per rank mapped into every
+        rank (torch.distributed._symmetric_memory = CUDA VMM + fabric handles: plumbing), its peer / multicast pointers and
+        signal pads handed to mfvae_comm_bind.  Returns False when symmetric memory cannot be set up on this machine."""
+        import torch.distributed as dist
+        mode = _os.environ.get("MFVAE_DP_COMM", "native")            # "nccl": the round-1 route (torch.distributed all_reduce)
+        if mode == "nccl":
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm
+            lib = L.lib()
+            bf16 = self.precision == "bf16" and _os.environ.get("MFVAE_DP_PAYLOAD", "bf16") != "fp32"
+            nbytes = lib.mfvae_comm_window_bytes(self._h, int(bf16))
+            group = process_group if process_group is not None else dist.group.WORLD
+            win = symm.empty(nbytes, dtype=torch.uint8, device=self._tdev)
+            win.zero_()
+            hdl = symm.rendezvous(win, group=group.group_name)
+            mc = int(hdl.multicast_ptr) if _os.environ.get("MFVAE_DP_MULTICAST", "1") != "0" else 0
+            L.check(lib.mfvae_comm_bind(self._h, hdl.rank, hdl.world_size, C.c_void_p(int(hdl.buffer_ptrs_dev)), C.c_void_p(mc) if mc else None,
+                                        C.c_void_p(int(hdl.signal_pad_ptrs_dev)), int(hdl.signal_pad_size), C.c_void_p(win.data_ptr()), nbytes,
+                                        int(bf16), int(_os.environ.get("MFVAE_DP_BLOCKS", "0"))))
+            self._comm_win, self._comm_hdl = win, hdl
+            self.comm_info = {"route": "native", "payload": "bf16" if bf16 else "fp32", "multicast": bool(mc), "window_bytes": int(nbytes)}
+            torch.cuda.synchronize(self._tdev)
+            dist.barrier(group=process_group)
+            return True
+        except Exception as e:                                        # no fabric / multicast support: keep the NCCL route
+            if mode == "native_strict":
+                raise
+            self.comm_info = {"route": "nccl", "why": f"{type(e).__name__}: {e}"[:200]}
+            return False
+
     def enable_data_parallel(self, process_group=None):
         import torch.distributed as dist
         if not dist.is_initialized():
@@ -703,8 +737,11 @@ class MAVAE(nn.Module):
             dist.broadcast(meta, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
             self._adam_t, self.philox_step, self.philox_seed = (int(x) for x in meta.cpu())
             self._dirty = True
+            self._native_comm = bool(self._on_gpu and self._bind_native_comm(process_group))
         if self._on_gpu and self._comm_stream is None:
-            self._comm_stream = torch.cuda.Stream(self._tdev)
+            # greatest priority: the exchange kernels are small and latency-critical, and every GEMM of backward is a persistent
+            # grid that owns all CTA slots -- a default-priority stream gets its CTAs in only at kernel boundaries, late
+            self._comm_stream = torch.cuda.Stream(self._tdev, priority=-1)
         if self._on_gpu and self.data_parallel:
             # SMs the persistent GEMM grids leave to the NCCL kernels running beside backward.  Measured at 2 GPUs: 0 / 16 / 32
             # reserved -> 1.091 / 1.084 / 1.113 ms per step (NCCL's CTAs co-reside with ours), so the default is 0.
@@ -743,7 +780,24 @@ class MAVAE(nn.Module):
         csp = C.c_void_p(cs.cuda_stream)
         if adam is not None:
             self._adam_t += 1
-        guarded = False
+        if self._native_comm and not _DP_DEBUG:
+            # the library's own exchange kernels: per bucket pack -> two-shot reduce over peer memory -> Adam from the window
+            lr, betas, eps = adam if adam is not None else (0.0, (0.9, 0.999), 1e-8)
+            if not self._losses_reduced:
+                L.check(lib.mfvae_loss_wait(self._h, csp))
+                L.check(lib.mfvae_allreduce_losses(self._h, csp))
+            self._losses_reduced = False
+            for i, b, e in buckets:
+                L.check(lib.mfvae_bucket_wait(self._h, i, csp))
+                if adam is not None:
+                    L.check(lib.mfvae_bucket_read_wait(self._h, i, csp))
+                e_opt = min(e, self._n_opt)
+                L.check(lib.mfvae_allreduce_grads(self._h, b, e_opt, int(adam is not None), float(lr), float(betas[0]), float(betas[1]),
+                                                  float(eps), max(self._adam_t, 1), csp))
+            main.wait_stream(cs)
+            if adam is not None:
+                L.check(lib.mfvae_opt_join(self._h, C.c_void_p(main.cuda_stream)))
+            return
         dbg = _DP_DEBUG            # measurement switches (MFVAE_DP_DEBUG): never set in production
         with torch.cuda.stream(cs):
             # the loss scalars are final before backward starts: reduce them first, beside backward, not in the step's tail
@@ -757,9 +811,7 @@ class MAVAE(nn.Module):
                 if "nocomm" not in dbg:
                     dist.all_reduce(self._grad[b:e], group=self._pg, async_op=True).wait()     # cs waits for NCCL
                 if adam is not None:
-                    if not guarded:     # backward may still be reading the decoder weights these buckets hold
-                        L.check(lib.mfvae_wait_decoder_reads(self._h, csp))
-                        guarded = True
+                    L.check(lib.mfvae_bucket_read_wait(self._h, i, csp))     # backward may still be reading this bucket's weights
                     lr, betas, eps = adam
                     L.check(lib.mfvae_adam_range(self._h, b, min(e, self._n_opt), float(lr), float(betas[0]), float(betas[1]),
                                                  float(eps), self._adam_t, csp))

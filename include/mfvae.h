@@ -213,7 +213,7 @@ int mfvae_bucket_wait(MfvaeHandle h, int32_t i, void* stream);
  *   multicast_window multicast (NVLS) mapping of the same windows, or NULL -> plain peer loads / stores
  *   d_signal_pads    device array [world] of zero-initialised 32-bit flag pads of signal_pad_bytes each (slots [0, 64) are not used)
  * payload_bf16 = 1 ships gradients as bf16 (the switch / the reducing rank accumulates in fp32); 0 ships fp32.
- * Every rank must issue the same sequence of mfvae_allreduce_* calls.  max_blocks (0 = 64) caps the CTAs of a reduce; one 32-bit
+ * Every rank must issue the same sequence of mfvae_allreduce_* calls.  max_blocks (0 = 128) caps the CTAs of a reduce; one 32-bit
  * flag per (CTA, peer) is used behind the first 64 slots of a pad, so signal_pad_bytes bounds it too. */
 int mfvae_comm_bind(MfvaeHandle h, int32_t rank, int32_t world, void* const* d_peer_windows, void* multicast_window,
                     void* const* d_signal_pads, int64_t signal_pad_bytes, void* local_window, int64_t window_bytes, int32_t payload_bf16,
@@ -223,7 +223,10 @@ int64_t mfvae_comm_window_bytes(MfvaeHandle h, int32_t payload_bf16);
  * Adam of that range right behind it (reduced gradient read from the window, fp32 copy left in the gradient arena) */
 int mfvae_allreduce_grads(MfvaeHandle h, int64_t begin, int64_t end, int32_t do_adam, float lr, float beta1, float beta2, float eps,
                           int64_t t, void* stream);
-/* do_adam = 1 sweeps run on an internal optimizer stream behind their reduce; this makes `stream` wait for all of them */
+/* do_adam = 1 sweeps run on an internal optimizer stream behind their reduce; this makes `stream` wait for all of them.
+ * A caller may skip it ("pipelined" step): the next mfvae_forward / mfvae_fwd_bwd on this handle waits for the sweeps itself,
+ * right before its decoder half -- the encoder half of the next step then overlaps the optimizer tail of this one.  Anything
+ * else that reads parameters (the host copying them out) must call mfvae_opt_join first. */
 int mfvae_opt_join(MfvaeHandle h, void* stream);
 /* sum over ranks of the 4 loss scalars of the step in flight, in place */
 int mfvae_allreduce_losses(MfvaeHandle h, void* stream);

@@ -122,9 +122,23 @@ struct CommArgs {
   uint32_t* const* pads;       // device array [world]: signal pads
 };
 
-// two-shot all-reduce of window bytes [byte0, byte1) (multiples of 16), in place in every window
+// two-shot all-reduce of window bytes [byte0, byte1) (multiples of 16), in place in every window.  With `src` the kernel first
+// packs this rank's fp32 gradients of the range into its window (no separate pack launch waiting for CTA slots).
 template <typename TP, bool MC>
-__global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommArgs c, int64_t byte0, int64_t byte1) {
+__global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommArgs c, int64_t byte0, int64_t byte1, const float* __restrict__ src) {
+  if (src) {
+    TP* w = reinterpret_cast<TP*>(static_cast<char*>(c.peers[c.rank]) + byte0);
+    const int64_t n4 = (byte1 - byte0) / (4 * static_cast<int64_t>(sizeof(TP)));
+    constexpr int UP = 4;
+    const int64_t pstride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += UP * pstride) {
+      float4 v[UP];
+#pragma unroll
+      for (int u = 0; u < UP; ++u) if (i + u * pstride < n4) v[u] = ldg_stream4(src + (i + u * pstride) * 4);
+#pragma unroll
+      for (int u = 0; u < UP; ++u) if (i + u * pstride < n4) store4<TP>(w + (i + u * pstride) * 4, v[u]);
+    }
+  }
   rank_barrier(c.pads, c.rank, c.world);                       // every rank's pack of this range has landed
   const int64_t nvec = (byte1 - byte0) >> 4;
   const int64_t per = (nvec + c.world - 1) / c.world;
@@ -279,20 +293,22 @@ int comm_unpack(const void* window, int dtype, float* g, int64_t begin, int64_t 
   return 0;
 }
 
-int comm_allreduce(const CommCtx& c, int64_t begin, int64_t end, cudaStream_t s) {
+int comm_allreduce(const CommCtx& c, int64_t begin, int64_t end, cudaStream_t s, const float* pack_from) {
   MFVAE_CHECK(begin % 8 == 0 && end % 8 == 0 && end >= begin, "comm: ranges must be 8-element aligned");
   if (end == begin) return 0;
   const int64_t es = (c.dtype == kBF16) ? 2 : 4;
   const int64_t b0 = begin * es, b1 = end * es;
   CommArgs a{c.rank, c.world, c.d_peers, static_cast<char*>(c.mc), c.d_pads};
-  const int64_t nvec_rank = ((b1 - b0) / 16 + c.world - 1) / c.world;
-  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(c.max_blocks, (nvec_rank + kCommThreads * 8 - 1) / (kCommThreads * 8))));
+  const float* src = pack_from ? pack_from + begin : nullptr;
+  // grid: enough CTAs for the pack of the whole range (every rank packs all of it), capped
+  const int64_t nvec = (b1 - b0) / 16;
+  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(c.max_blocks, (nvec + kCommThreads * 8 - 1) / (kCommThreads * 8))));
   if (c.dtype == kBF16) {
-    if (c.mc) allreduce_kernel<__nv_bfloat16, true><<<blocks, kCommThreads, 0, s>>>(a, b0, b1);
-    else      allreduce_kernel<__nv_bfloat16, false><<<blocks, kCommThreads, 0, s>>>(a, b0, b1);
+    if (c.mc) allreduce_kernel<__nv_bfloat16, true><<<blocks, kCommThreads, 0, s>>>(a, b0, b1, src);
+    else      allreduce_kernel<__nv_bfloat16, false><<<blocks, kCommThreads, 0, s>>>(a, b0, b1, src);
   } else {
-    if (c.mc) allreduce_kernel<float, true><<<blocks, kCommThreads, 0, s>>>(a, b0, b1);
-    else      allreduce_kernel<float, false><<<blocks, kCommThreads, 0, s>>>(a, b0, b1);
+    if (c.mc) allreduce_kernel<float, true><<<blocks, kCommThreads, 0, s>>>(a, b0, b1, src);
+    else      allreduce_kernel<float, false><<<blocks, kCommThreads, 0, s>>>(a, b0, b1, src);
   }
   MFVAE_LAUNCH_CHECK();
   return 0;

@@ -109,7 +109,7 @@ struct CommCtx {
 };
 int comm_pack(const float* g, void* window, int dtype, int64_t begin, int64_t end, cudaStream_t s);
 int comm_unpack(const void* window, int dtype, float* g, int64_t begin, int64_t end, cudaStream_t s);
-int comm_allreduce(const CommCtx& c, int64_t begin, int64_t end, cudaStream_t s);
+int comm_allreduce(const CommCtx& c, int64_t begin, int64_t end, cudaStream_t s, const float* pack_from = nullptr);   // pack_from: fp32 arena whose [begin, end) is packed first
 int comm_allreduce_scalars(const CommCtx& c, const float* src, int n, float* out, cudaStream_t s);
 int comm_small_allreduce_adam(const CommCtx& c, int64_t n, float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, int do_adam,
                               float lr, float b1, float b2, float eps, int64_t t, cudaStream_t s);

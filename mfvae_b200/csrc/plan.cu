@@ -93,6 +93,7 @@ struct MfvaeHandle_ {
   // third stream: the reward head (two tiny GEMM chains) and the action-embedding kernels run beside the big layers
   cudaStream_t aux = nullptr;
   bool grads_zeroed = false;                 // mfvae_fwd_bwd: the gradient arena was zeroed on csum beside the forward pass
+  bool opt_pending = false;                  // optimizer sweeps on opt_stream that no stream of the next forward has waited for yet
   bool sout_bias_done = false;               // the state head's bias gradient was accumulated by the loss kernel (mfvae_fwd_bwd)
   cudaEvent_t zero_ev = nullptr, zero_fork_ev = nullptr;
   cudaEvent_t loss_ev = nullptr;             // the four loss scalars are final (recorded at the end of the loss phase)
@@ -517,6 +518,7 @@ static int enc_bias_on(MfvaeHandle_* h, cudaStream_t q) {
 static int do_forward_act_embed(MfvaeHandle_* h, const StageArgs& st, cudaStream_t s, bool fold_i) {
   if (!use_aux(h)) {
     if (fold_i) MFVAE_TRY(enc_bias_on(h, s));
+    if (h->opt_pending) { MFVAE_CUDA(cudaStreamWaitEvent(s, h->opt_ev, 0)); h->opt_pending = false; }
     return act_embed_on(h, st, s);
   }
   MFVAE_CUDA(cudaEventRecord(h->aux_fork_ev, s));          // orders it after whatever last read ZIN on the caller's stream
@@ -525,6 +527,9 @@ static int do_forward_act_embed(MfvaeHandle_* h, const StageArgs& st, cudaStream
     MFVAE_TRY(enc_bias_on(h, h->aux));
     MFVAE_CUDA(cudaEventRecord(h->eb_ev, h->aux));
   }
+  // a pipelined optimizer sweep of the decoder block (mfvae_allreduce_grads without mfvae_opt_join) may still be running:
+  // the encoder half of this forward does not read what it writes, the action fold (decoder layer 0's master weights) does
+  if (h->opt_pending) MFVAE_CUDA(cudaStreamWaitEvent(h->aux, h->opt_ev, 0));
   MFVAE_TRY(act_embed_on(h, st, h->aux));
   MFVAE_CUDA(cudaEventRecord(h->aux_join_ev, h->aux));
   return 0;
@@ -535,6 +540,7 @@ static int do_forward_act_embed(MfvaeHandle_* h, const StageArgs& st, cudaStream
 static int do_forward_decoders(MfvaeHandle_* h, cudaStream_t s, const MfvaeBatch* loss_batch = nullptr, int huber = 1, bool recon16 = false,
                                bool defer_reward_join = false) {
   const bool aux = use_aux(h);
+  if (h->opt_pending) { MFVAE_CUDA(cudaStreamWaitEvent(s, h->opt_ev, 0)); h->opt_pending = false; }
   if (aux) MFVAE_CUDA(cudaStreamWaitEvent(s, h->aux_join_ev, 0));     // action embeddings are in ZIN
   for (int l = 0; l < h->cfg.n_dec_hidden; ++l) MFVAE_TRY(run_gemm(h, h->g_dec_fwd[l], s));
   // reward head (two tiny GEMMs) beside the state output layer.  It is enqueued FIRST: the output layer is a persistent
@@ -1149,7 +1155,7 @@ int mfvae_comm_bind(MfvaeHandle h, int32_t rank, int32_t world, void* const* d_p
   // one 32-bit flag per (block, peer) behind the 64 slots left to the host framework
   const int64_t slot_blocks = (signal_pad_bytes / 4 - 64) / world;
   MFVAE_CHECK(slot_blocks >= 1, "comm: signal pads too small (need >= 256 + 4 * world bytes)");
-  c.max_blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(max_blocks > 0 ? max_blocks : 64, slot_blocks), kNumSMs)));
+  c.max_blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(max_blocks > 0 ? max_blocks : 128, slot_blocks), kNumSMs)));
   for (auto& e : h->ar_ev) if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   return 0;
 }
@@ -1173,8 +1179,7 @@ int mfvae_allreduce_grads(MfvaeHandle h, int64_t begin, int64_t end, int32_t do_
     return comm_small_allreduce_adam(c, e8 - begin, h->ar.d_param + begin, h->ar.d_grad + begin, h->ar.d_m + begin, h->ar.d_v + begin,
                                      sh ? sh + begin : nullptr, do_adam, lr, beta1, beta2, eps, t, s);
   }
-  MFVAE_TRY(comm_pack(h->ar.d_grad, c.local, c.dtype, begin, e8, s));
-  MFVAE_TRY(comm_allreduce(c, begin, e8, s));
+  MFVAE_TRY(comm_allreduce(c, begin, e8, s, h->ar.d_grad));       // pack (fp32 -> payload) + two-shot reduce, one kernel
   if (do_adam) {
     // the optimizer sweep of this range runs on the handle's optimizer stream behind the reduce, so that the next bucket's
     // reduce (on `stream`) does not queue behind a 100-200 MB sweep; mfvae_opt_join makes the caller's stream wait for it
@@ -1188,7 +1193,7 @@ int mfvae_allreduce_grads(MfvaeHandle h, int64_t begin, int64_t end, int32_t do_
     }
     MFVAE_TRY(launch_adam_payload(h->ar.d_param + begin, static_cast<const char*>(c.local) + begin * es, c.dtype, h->ar.d_grad + begin,
                                   h->ar.d_m + begin, h->ar.d_v + begin, sh ? sh + begin : nullptr, e8 - begin, lr, beta1, beta2, eps, t, o));
-    if (o != s) MFVAE_CUDA(cudaEventRecord(h->opt_ev, o));
+    if (o != s) { MFVAE_CUDA(cudaEventRecord(h->opt_ev, o)); h->opt_pending = true; }
     return 0;
   }
   return comm_unpack(c.local, c.dtype, h->ar.d_grad, begin, e8, s);
@@ -1197,6 +1202,7 @@ int mfvae_allreduce_grads(MfvaeHandle h, int64_t begin, int64_t end, int32_t do_
 int mfvae_opt_join(MfvaeHandle h, void* stream) {
   MFVAE_CHECK(h, "null handle");
   if (h->opt_stream && h->opt_ev) MFVAE_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->opt_ev, 0));
+  h->opt_pending = false;
   return 0;
 }
 // sum of the 4 loss scalars of the step in flight across ranks (in place in the handle's loss slots), on `stream`

@@ -314,6 +314,7 @@ class MAVAE(nn.Module):
         self._last_mu = self._last_lv = None
         self._comm_stream = None
         self._native_comm = False
+        self._opt_pending = False
         self.comm_info = {"route": "none"}
 
     # ------------------------------------------------------------------ construction helpers
@@ -436,6 +437,7 @@ class MAVAE(nn.Module):
         """Reference model.py:175-176: ``torch.save(self.state_dict(), path)`` -- the 39 registered tensors only (the
         per-agent encoders and action tables live in plain dicts there and are NOT saved).  The file loads with
         ``strict=True`` into the reference ``MAVAE`` and back."""
+        self.synchronize_optimizer()
         torch.save(self.state_dict(), path)
 
     # ---- the checkpoint the reference forgets (SURVEY section 8f-2): everything needed to resume bit-identically ----
@@ -445,6 +447,7 @@ class MAVAE(nn.Module):
         """``state_dict`` (the reference's 39 keys, loadable by the reference itself) + the unregistered per-agent encoders /
         action tables under the oracle's names + Adam exp_avg / exp_avg_sq / step of the optimised prefix + the Philox
         (seed, step) of the reparameterisation stream.  CPU tensors."""
+        self.synchronize_optimizer()
         n = self._n_opt
         sd = {k: v.detach().cpu().clone() for k, v in self.state_dict().items()}
         extra = {k: p.detach().cpu().clone() for k, p in self.named_arena_tensors().items() if k not in sd}
@@ -521,6 +524,7 @@ class MAVAE(nn.Module):
             return
         v = self._arena._version
         if v != self._arena_version or self._dirty:
+            self.synchronize_optimizer()
             L.check(L.lib().mfvae_refresh_shadow(self._h, self._stream()))
             self._arena_version = v
             self._dirty = False
@@ -759,7 +763,15 @@ class MAVAE(nn.Module):
                 out.append((i, b.value, e.value))
         return out
 
-    def _allreduce_grads(self, adam=None):
+    def synchronize_optimizer(self):
+        """Order the current stream behind every optimizer sweep a pipelined ``train_step(..., pipeline=True)`` left in flight.
+        ``forward`` / ``train_step`` / ``test_step`` / ``adam_step`` / checkpointing do it themselves; call it before reading
+        parameter tensors directly after a pipelined step."""
+        if self._opt_pending and self._on_gpu:
+            L.check(L.lib().mfvae_opt_join(self._h, self._stream()))
+        self._opt_pending = False
+
+    def _allreduce_grads(self, adam=None, pipeline=False):
         """SUM all-reduce of the gradient buckets (the loss-gradient kernels already divide by the GLOBAL batch, so
         no averaging pass is needed) and of the 4 partial loss scalars.  On the GPU each bucket is reduced on the
         communication stream as soon as its completion event fires, overlapping the rest of backward; with
@@ -796,7 +808,10 @@ class MAVAE(nn.Module):
                                                   float(eps), max(self._adam_t, 1), csp))
             main.wait_stream(cs)
             if adam is not None:
-                L.check(lib.mfvae_opt_join(self._h, C.c_void_p(main.cuda_stream)))
+                if pipeline:
+                    self._opt_pending = True        # joined by the next forward inside the library, or by synchronize_optimizer()
+                else:
+                    L.check(lib.mfvae_opt_join(self._h, C.c_void_p(main.cuda_stream)))
             return
         dbg = _DP_DEBUG            # measurement switches (MFVAE_DP_DEBUG): never set in production
         with torch.cuda.stream(cs):
@@ -825,6 +840,7 @@ class MAVAE(nn.Module):
         ``overlapped`` (single GPU, called right after backward): the decoder block is updated on an internal stream
         as soon as its gradients are final, concurrently with the encoder half of backward."""
         self._require_gpu()
+        self.synchronize_optimizer()
         self._adam_t += 1
         self._grads_pending = False
         fn = L.lib().mfvae_adam_step_overlapped if overlapped else L.lib().mfvae_adam_step
@@ -850,10 +866,13 @@ class MAVAE(nn.Module):
             dist.all_reduce(self._losses, group=self._pg)
         return self._losses
 
-    def train_step(self, pb: PackedBatch, lr: float, betas=(0.9, 0.999), eps=1e-8, loss_weights=None):
+    def train_step(self, pb: PackedBatch, lr: float, betas=(0.9, 0.999), eps=1e-8, loss_weights=None, pipeline=False):
         """Fast path: forward + fused ELBO + backward (+ all-reduce) + Adam, no autograd graph.
         Returns the device tensor [loss, s_loss, r_loss, kl_loss].  ``loss_weights`` = (kl_weight, r_weight[, s_weight])
-        overrides the module globals (e.g. the jax_ver weighting (0.1, 0.5, 0.5))."""
+        overrides the module globals (e.g. the jax_ver weighting (0.1, 0.5, 0.5)).
+        ``pipeline`` (data parallel): return without ordering the caller's stream behind the decoder block's optimizer sweep;
+        the next step's encoder half then overlaps it (the library orders the decoder half itself).  See
+        ``synchronize_optimizer`` before touching parameter tensors by hand."""
         self._require_gpu()
         lib = L.lib()
         self._bind(pb.batch)
@@ -867,7 +886,7 @@ class MAVAE(nn.Module):
         self._losses = self._ws_view(out.d_losses, 1, 4, 4)[0]
         self.philox_step += 1
         if self.data_parallel:
-            self._allreduce_grads(adam=(lr, betas, eps))      # per-bucket all-reduce + Adam on the communication stream
+            self._allreduce_grads(adam=(lr, betas, eps), pipeline=pipeline)      # per-bucket all-reduce + Adam on the communication stream
         else:
             self.adam_step(lr, betas, eps, overlapped=True)
         return self._losses

@@ -328,7 +328,8 @@ def run_ours(args, w):
     spec = make_spec(w)
     B = args.batch or w["batch"]
     m = M.MAVAE(spec.idx_features, spec.latent, spec.act_features, True, spec.agents, spec.obs_dim, spec.n_act, dev,
-                precision=w["precision"], enc_hidden=w["enc_hidden"], dec_hidden=w["dec_hidden"], include_dead_decoder=False)
+                precision=w["precision"], enc_hidden=w["enc_hidden"], dec_hidden=w["dec_hidden"], include_dead_decoder=False,
+                fusion=os.environ.get("MFVAE_FUSION", "auto"))
     torch.manual_seed(0)
     m.reset_parameters()
     if world > 1:

@@ -35,11 +35,12 @@ enum { MFVAE_ENGINE_AUTO = 0, MFVAE_ENGINE_SIMT = 1, MFVAE_ENGINE_TCGEN05 = 2 };
 /* Cross-layer fusions of the tcgen05 engine (bit mask).  All variants compute the same values with the same rounding
  * points; tests/test_gpu_fused.py pins them against each other.
  *   NONE     one kernel per layer
- *   ENCODER  staging + the per-agent encoder chain + reparameterisation + KL as ONE persistent tcgen05 kernel
- *            (enc_fused.cu; per-layer kernels are used when its shape constraints do not hold)
+ *   ENCODER  the per-agent encoder chain + reparameterisation + KL as ONE persistent tcgen05 kernel on the staged [obs | 0]
+ *            tile (enc_fused.cu; per-layer kernels are used when its shape constraints do not hold, or when the batch carries
+ *            an explicit per-row agent-index column, which cannot be folded into layer 0's bias)
  *   LOSS     mfvae_fwd_bwd only: the state head's reconstruction loss and its gradient are the epilogue of the output-layer
  *            GEMM (recon_s is never written to HBM; MfvaeOutputs.d_recon_s is NULL)
- *   AUTO     the combination that measured fastest on B200 (today: NONE)
+ *   AUTO     the combination that measured fastest on B200 (today: ENCODER)
  *   NOFOLD_IDX / NOFOLD_ACT   keep a constant-input column block dense (csrc/fold.cu): the id-embedding columns of encoder
  *            layer 0 (instead of a per-agent bias) / the action-embedding half of decoder layer 0 (K = A*C instead of
  *            A*n_act one-hot columns).  Same mathematics, different bf16 rounding points; used by the tests that pin the

@@ -1,19 +1,22 @@
-// enc_fused.cu — the 40 per-agent encoders as ONE persistent tcgen05 kernel per direction (sm_100a).
+// enc_fused.cu — the 40 per-agent encoders as ONE persistent tcgen05 kernel (sm_100a), two CTAs per SM.
 //
-// Reference being reproduced (torch_ver/model.py): per agent, idx_emb lookup + cat with the observation (:142-143),
-// Encoder MLP in -> 64 -> 64 -> 256 -> 2L with ReLU (:43-57,144), mu / logvar split (:149-150), reparameterize
-// (:77-81,151) and the agent's KL term (:35-37).  Layer by layer these are 160 tiny GEMMs whose activations make a
-// round trip through HBM each; here one CTA owns a (agent, 128-sample tile) unit and chains the layers on chip:
+// Reference being reproduced (torch_ver/model.py): per agent, Encoder MLP in -> 64 -> 64 -> 256 -> 2L with ReLU (:43-57,144),
+// mu / logvar split (:149-150), reparameterize (:77-81,151) and the agent's KL term (:35-37).  Layer by layer these are 160
+// tiny GEMMs whose activations make a round trip through HBM each; here one CTA owns a (agent, 128-sample tile) unit and
+// chains the layers on chip.  The id-embedding is folded into layer 0's bias (fold.cu), so the unit's input is the staged
+// bf16 tile X0F = [obs | 0] the backward pass needs anyway:
 //
-//   workers (8 warps)   build X0 = [idx_emb | obs_a | 0] as bf16 straight into 128B-swizzled shared memory, later run every
-//                       layer's epilogue: TMEM -> +bias -> ReLU -> bf16 -> shared memory (the next layer's A operand, written
-//                       in place over the previous activation) and, for the last layer, mu / logvar -> reparameterize -> z, KL
-//   control (1 thread)  TMA-loads the agent's four weight matrices once per agent (they stay resident in shared memory),
-//                       issues each layer's tcgen05.mma chain into its own TMEM columns, and TMA-stores every activation
-//                       tile to HBM (the backward pass needs them) while the MMAs that read the same tile run
+//   control (1 thread)  TMA-loads the unit's X0F tile and, layer by layer, that layer's weight matrix into ONE 32 KB buffer
+//                       (streamed from L2 per unit: nothing agent-sized stays resident, which is what lets two CTAs share an
+//                       SM and hide each other's latencies), issues each layer's tcgen05.mma chain into the SAME TMEM columns
+//                       (layer l+1 starts only after layer l's epilogue has drained them), and TMA-stores every hidden
+//                       activation tile to HBM for the backward pass while the MMAs that read the same tile run
+//   workers (8 warps)   every layer's epilogue: TMEM -> +bias -> ReLU -> bf16 -> shared memory (the next layer's A operand) and,
+//                       for the last layer, mu / logvar -> LAT, reparameterize -> z, KL partial
 //
-// Synchronisation is mbarriers only: act_ready[l] (workers -> control: layer l's input is in shared memory),
-// mma_done[l] (tcgen05.commit -> workers: layer l's accumulator is complete AND its input tile may be overwritten).
+// Synchronisation is mbarriers only: x0_full / w_full (TMA -> control), act_ready[l] (workers -> control: layer l's input is in
+// shared memory), mma_done[l] (tcgen05.commit -> workers and control), tmem_free (workers -> control: the last layer's
+// accumulator has been read, the next unit's layer 0 may overwrite it).
 #include <cuda.h>
 
 #include <algorithm>
@@ -29,21 +32,16 @@ constexpr int kBoxBytes = kEncRows * 128;      // one [128 rows x 64 bf16] swizz
 constexpr int kActBoxes = 4;                   // activations up to 256 columns wide
 constexpr int kEncWorkers = 256;
 constexpr int kEncThreads = kEncWorkers + 32;  // + the control warp
-constexpr int kEncTmemCols = 512;
-constexpr size_t kEncSmemLimit = 227 * 1024 - 1024;   // dynamic + static shared memory must fit 227 KB per CTA
+constexpr int kEncTmemCols = 256;              // one accumulator region, reused by every layer
+constexpr size_t kEncSmemLimit = 113 * 1024 - 1024;   // two CTAs per SM
 
 struct EncFwdParams {
   int A, B, tiles, total_units, nl;
-  int N[kEncMaxL], kboxes[kEncMaxL], ksteps[kEncMaxL], tmem_col[kEncMaxL];
-  int in_box[kEncMaxL], wait_store[kEncMaxL];   // first activation box of layer l's input; 1: its TMA store must drain before the epilogue
-  uint32_t w_off[kEncMaxL], w_bytes;           // weight offsets inside the weight region / its size
-  int bias_n;                                  // sum of N_l (= TMEM columns in use): bias l lives at [tmem_col[l], +N_l)
-  const float* bias[kEncMaxL];                 // [A][N_l] fp32
-  const float* obs; long long obs_ld;
-  const float* idx; int idx_ld;                // optional explicit agent-index column [B][A]
-  const float* idx_emb; int I;
-  const int32_t* obs_off; const int32_t* obs_dim;
-  __nv_bfloat16* xout[kEncMaxL]; long long xout_gs[kEncMaxL], xout_ld[kEncMaxL]; int xout_w[kEncMaxL];   // input of layer l in HBM
+  int N[kEncMaxL], kboxes[kEncMaxL], ksteps[kEncMaxL];
+  int in_box[kEncMaxL], wait_store[kEncMaxL];   // first activation box of layer l's input; 1: pending TMA stores must drain before the epilogue
+  uint32_t w_bytes[kEncMaxL], w_buf;           // bytes of layer l's weight boxes / size of the streaming buffer
+  int bias_off[kEncMaxL], bias_n;              // bias l lives at [bias_off[l], +N_l) of the per-agent bias block
+  const float* bias[kEncMaxL];                 // [A][N_l] fp32 (layer 0: the folded bias b0 + W0[:, :I] . emb[a])
   float* lat; long long lat_gs, lat_ld;
   __nv_bfloat16* zin; long long zin_ld;
   const float* eps; long long eps_ld;
@@ -53,38 +51,33 @@ struct EncFwdParams {
 };
 struct alignas(64) EncMaps { CUtensorMap w[kEncMaxL]; CUtensorMap x[kEncMaxL]; };
 
-enum { kStageNone = 0, kStageEmb, kStageEmbIdx, kStageVec, kStageScalar, kStageZero };
-struct StageLane {                             // one lane's role in building X0 rows of the unit being staged
-  int kind, a, b0, nvalid, off;
-  const float* src0;
-  uint4 emb;
-};
-
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  return make_uint4(pack_bf16x2(f[0], f[1], false), pack_bf16x2(f[2], f[3], false), pack_bf16x2(f[4], f[5], false),
-                    pack_bf16x2(f[6], f[7], false));
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
 }
 
-__global__ void __launch_bounds__(kEncThreads, 1)
+__global__ void __launch_bounds__(kEncThreads, 2)
 enc_fwd_kernel(const __grid_constant__ EncMaps maps, const EncFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ float red[32];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* act = smem;                                    // [4][16 KB]: X0, then every hidden activation, in place
-  uint8_t* wsm = smem + kActBoxes * kBoxBytes;            // the agent's weight matrices, K-major boxes of [N_l x 64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + p.w_bytes);
-  uint64_t* act_ready = bars;
-  uint64_t* mma_done = bars + kEncMaxL;
+  uint8_t* act = smem;                                    // [4][16 KB]: X0F, then every hidden activation
+  uint8_t* wsm = smem + kActBoxes * kBoxBytes;            // the current layer's weight matrix, K-major boxes of [N_l x 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + p.w_buf);
+  uint64_t* act_ready = bars;                             // [kEncMaxL]  ([0] unused: layer 0's input arrives by TMA)
+  uint64_t* mma_done = bars + kEncMaxL;                   // [kEncMaxL]
   uint64_t* w_full = bars + 2 * kEncMaxL;
-  uint64_t* store_done = bars + 2 * kEncMaxL + 1;           // control -> workers: the last activation store has left shared memory
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kEncMaxL + 2);
-  float* bias_s = reinterpret_cast<float*>(bars + 16);               // 128 bytes in: 16-byte aligned   // [2][bias_n]: the agent's biases, double-buffered
+  uint64_t* x0_full = bars + 2 * kEncMaxL + 1;
+  uint64_t* tmem_free = bars + 2 * kEncMaxL + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kEncMaxL + 3);
+  float* bias_s = reinterpret_cast<float*>(bars + 16);    // 128 bytes in: 16-byte aligned; [2][bias_n], double-buffered per agent
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int l = 0; l < kEncMaxL; ++l) { mbar_init(act_ready + l, kEncWorkers); mbar_init(mma_done + l, 1); }
     mbar_init(w_full, 1);
-    mbar_init(store_done, 1);
+    mbar_init(x0_full, 1);
+    mbar_init(tmem_free, kEncWorkers);
     fence_barrier_init();
   }
   if (warp == 8) {
@@ -104,43 +97,56 @@ enc_fwd_kernel(const __grid_constant__ EncMaps maps, const EncFwdParams p) {
 
   if (warp == 8) {
     // ================================ control thread ================================
-    if (lane == 0) {
+    if (lane == 0 && u0 < u1) {
       uint32_t par = 0, wpar = 0;
-      int cur_a = -1;
       const uint32_t act_s = smem_u32(act), w_s = smem_u32(wsm);
+      auto load_w = [&](int l, int a) {
+        mbar_expect_tx(w_full, p.w_bytes[l]);
+        for (int kb = 0; kb < p.kboxes[l]; ++kb) tma_load_3d(wsm + kb * p.N[l] * 128, &maps.w[l], w_full, kb * 64, 0, a);
+      };
+      auto load_x0 = [&](int u) {
+        const int a = u / p.tiles, t = u - a * p.tiles;
+        mbar_expect_tx(x0_full, static_cast<uint32_t>(p.kboxes[0]) * kBoxBytes);
+        for (int kb = 0; kb < p.kboxes[0]; ++kb) tma_load_3d(act + kb * kBoxBytes, &maps.x[0], x0_full, kb * 64, t * kEncRows, a);
+      };
+      load_x0(u0);
+      load_w(0, u0 / p.tiles);
       for (int u = u0; u < u1; ++u, par ^= 1) {
         const int a = u / p.tiles, t = u - a * p.tiles;
-        if (a != cur_a) {                      // every MMA of the previous unit has retired (wait at the loop's end)
-          cur_a = a;
-          mbar_expect_tx(w_full, p.w_bytes);
-          for (int l = 0; l < nl; ++l)
-            for (int kb = 0; kb < p.kboxes[l]; ++kb)
-              tma_load_3d(wsm + p.w_off[l] + kb * p.N[l] * 128, &maps.w[l], w_full, kb * 64, 0, a);
-          mbar_wait(w_full, wpar); wpar ^= 1;
-        }
         for (int l = 0; l < nl; ++l) {
-          mbar_wait(act_ready + l, par);
+          mbar_wait(w_full, wpar); wpar ^= 1;
+          if (l == 0) {
+            mbar_wait(x0_full, par);
+            if (u > u0) mbar_wait(tmem_free, par ^ 1);          // the previous unit's last accumulator has been read
+          } else {
+            mbar_wait(act_ready + l, par);
+          }
           tc_fence_after();
           const uint32_t in_s = act_s + p.in_box[l] * kBoxBytes;
-          {              // layer l's input tile: out to HBM for the backward pass while the MMAs below read the same bytes
+          if (l > 0) {   // layer l's input tile: out to HBM for the backward pass while the MMAs below read the same bytes
             for (int kb = 0; kb < p.kboxes[l]; ++kb)
               tma_store_3d(&maps.x[l], act + (p.in_box[l] + kb) * kBoxBytes, kb * 64, t * kEncRows, a);
             tma_store_commit();
           }
           const uint32_t idesc = make_idesc(kEncRows, p.N[l], false, false);
-          const uint32_t wl = w_s + p.w_off[l];
           const uint32_t nbox = static_cast<uint32_t>(p.N[l]) * 128u;
           for (int ks = 0; ks < p.ksteps[l]; ++ks) {
             const uint64_t da = make_smem_desc(in_s + (ks >> 2) * kBoxBytes + (ks & 3) * 32, 16u, 1024u);
-            const uint64_t db = make_smem_desc(wl + (ks >> 2) * nbox + (ks & 3) * 32, 16u, 1024u);
-            umma_bf16(tmem_base + p.tmem_col[l], da, db, idesc, ks > 0 ? 1u : 0u);
+            const uint64_t db = make_smem_desc(w_s + (ks >> 2) * nbox + (ks & 3) * 32, 16u, 1024u);
+            umma_bf16(tmem_base, da, db, idesc, ks > 0 ? 1u : 0u);
           }
           if (p.wait_store[l]) tma_store_wait_read();   // this layer's epilogue writes over boxes a store may still be reading
           umma_commit(mma_done + l);
+          // the weight buffer (and, after the last layer, the activation boxes) are free once these MMAs have retired
+          mbar_wait(mma_done + l, par);
+          if (l + 1 < nl) {
+            load_w(l + 1, a);
+          } else if (u + 1 < u1) {
+            tma_store_wait_read();                      // the last hidden activation's store has left shared memory
+            load_x0(u + 1);
+            load_w(0, (u + 1) / p.tiles);
+          }
         }
-        tma_store_wait_read();
-        mbar_arrive(store_done);                        // the next unit's X0 may overwrite the activation boxes
-        mbar_wait(mma_done + (nl - 1), par);
       }
       tma_store_wait_all();
     }
@@ -149,116 +155,29 @@ enc_fwd_kernel(const __grid_constant__ EncMaps maps, const EncFwdParams p) {
     const int q = warp & 3, half = warp >> 2;
     const int row = q * 32 + lane;                                   // tile row == TMEM lane
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const int nchunk0 = p.kboxes[0] * 8;                             // 16-byte chunks per X0 row held in shared memory
-    const int col0 = lane * 8;                                       // this lane's X0 columns [col0, col0 + 8)
-    uint8_t* const x0box = act + (lane >> 3) * kBoxBytes;
-    // staging state of the unit being prefetched: lane role + packed bf16 chunks of its 16 rows (warp + 8 i)
-    StageLane sl;
-    float raw[8][8];
-    int st_a = -1, st_bias = 0;
-    auto stage_setup = [&](int u) {
-      const int a = u / p.tiles, t = u - a * p.tiles;
-      if (a != st_a) {
-        st_a = a;
-        // the agent's biases -> shared memory (the other buffer may still be in use by the unit in flight)
-        st_bias ^= 1;
-        float* bs = bias_s + st_bias * p.bias_n;
-        for (int l = 0; l < nl; ++l)
-          for (int i = threadIdx.x; i < p.N[l]; i += kEncWorkers) bs[p.tmem_col[l] + i] = __ldg(p.bias[l] + static_cast<long long>(a) * p.N[l] + i);
-        asm volatile("bar.sync 1, %0;" ::"n"(kEncWorkers) : "memory");
-        const int od = p.obs_dim[a];
-        sl.nvalid = min(8, od - (col0 - p.I));
-        sl.off = p.obs_off[a] + (col0 - p.I);
-        sl.emb = make_uint4(0, 0, 0, 0);
-        if (!p.idx && col0 < p.I) {
-          float e[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) e[k] = __ldg(p.idx_emb + static_cast<long long>(a) * p.I + col0 + k);
-          sl.emb = pack8(e);
-        }
-      }
-      sl.a = a; sl.b0 = t * kEncRows;
-      sl.src0 = p.obs + static_cast<long long>(sl.b0) * p.obs_ld + sl.off;
-      sl.kind = kStageNone;
-      if (lane < nchunk0) {
-        if (col0 < p.I) sl.kind = p.idx ? kStageEmbIdx : kStageEmb;
-        else if (sl.nvalid > 0 && ((reinterpret_cast<uintptr_t>(sl.src0) | (static_cast<uintptr_t>(p.obs_ld) << 2)) & 7) == 0) sl.kind = kStageVec;
-        else if (sl.nvalid > 0) sl.kind = kStageScalar;
-        else sl.kind = kStageZero;
-      }
-    };
-    // global loads of half h (rows warp + 8 (8 h + i)) into `raw`: straight-line, all in flight together
-    auto stage_load = [&](int h) {
-      if (sl.kind == kStageVec) {
-        // 8-byte loads; the lane at the end of the agent's slice predicates the pairs past it (never reads beyond the row)
-        const int npair = sl.nvalid >> 1;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = min(warp + 8 * (8 * h + i), p.B - 1 - sl.b0);     // rows past the batch re-read its last row
-          const float* src = sl.src0 + static_cast<long long>(r) * p.obs_ld;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float2 v2 = make_float2(0.f, 0.f);
-            if (k < npair) v2 = __ldg(reinterpret_cast<const float2*>(src) + k);
-            else if (2 * k < sl.nvalid) v2.x = __ldg(src + 2 * k);
-            raw[i][2 * k] = v2.x; raw[i][2 * k + 1] = v2.y;
-          }
-        }
-      } else if (sl.kind == kStageScalar) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = min(warp + 8 * (8 * h + i), p.B - 1 - sl.b0);
-          const float* src = sl.src0 + static_cast<long long>(r) * p.obs_ld;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) raw[i][k] = (k < sl.nvalid) ? __ldg(src + k) : 0.f;
-        }
-      } else if (sl.kind == kStageEmbIdx) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const long long b = min(static_cast<long long>(sl.b0 + warp + 8 * (8 * h + i)), static_cast<long long>(p.B - 1));
-          const int id = max(0, min(static_cast<int>(__ldg(p.idx + b * p.idx_ld + sl.a)), p.A - 1));
-#pragma unroll
-          for (int k = 0; k < 8; ++k) raw[i][k] = __ldg(p.idx_emb + static_cast<long long>(id) * p.I + col0 + k);
-        }
-      }
-    };
-    // pack half h and write it to shared memory (A operand of layer 0; the control thread TMA-stores the tile to HBM)
-    auto stage_store = [&](int h) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = warp + 8 * (8 * h + i);
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (sl.kind == kStageEmb) v = sl.emb;
-        else if (sl.kind == kStageVec || sl.kind == kStageScalar || sl.kind == kStageEmbIdx) v = pack8(raw[i]);
-        if (sl.b0 + r >= p.B) v = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(x0box + sw128_chunk_off(r, lane & 7)) = v;
-      }
-    };
-
+    int cur_a = -1, bsel = 0;
     uint32_t par = 0;
     for (int u = u0; u < u1; ++u, par ^= 1) {
-      stage_setup(u);
-      const int a = sl.a, b0 = sl.b0;
-      const float* const bias_u = bias_s + st_bias * p.bias_n;
-      // ---- X0 = [idx_emb | obs_a | 0]: two batches of 8 rows per warp, each one DRAM round trip ----
-      if (u > u0) mbar_wait(store_done, par ^ 1);                    // previous unit's last activation store has drained
-      if (sl.kind != kStageNone) {
-        stage_load(0); stage_store(0);
-        stage_load(1); stage_store(1);
+      const int a = u / p.tiles, b0 = (u - a * p.tiles) * kEncRows;
+      if (a != cur_a) {
+        // the agent's biases -> shared memory (the other buffer may still be in use by slower warps of the previous unit)
+        cur_a = a; bsel ^= 1;
+        float* bs = bias_s + bsel * p.bias_n;
+        for (int l = 0; l < nl; ++l)
+          for (int i = threadIdx.x; i < p.N[l]; i += kEncWorkers) bs[p.bias_off[l] + i] = __ldg(p.bias[l] + static_cast<long long>(a) * p.N[l] + i);
+        asm volatile("bar.sync 1, %0;" ::"n"(kEncWorkers) : "memory");
       }
-      fence_proxy_async();
-      mbar_arrive(act_ready + 0);
-
-      // ---- hidden layers: accumulator -> +bias -> relu -> bf16 -> the next layer's A operand (in place) + HBM ----
+      const float* const bias_u = bias_s + bsel * p.bias_n;
+      // ---- hidden layers: accumulator -> +bias -> relu -> bf16 -> the next layer's A operand ----
       for (int l = 0; l + 1 < nl; ++l) {
         mbar_wait(mma_done + l, par);
         tc_fence_after();
         const int nch = p.N[l] >> 5;
-        const float* bias = bias_u + p.tmem_col[l];
+        const float* bias = bias_u + p.bias_off[l];
         uint8_t* const outb = act + p.in_box[l + 1] * kBoxBytes;
         for (int c = half; c < nch; c += 2) {
           uint32_t v[32];
-          tmem_ld32(lane_addr + p.tmem_col[l] + c * 32, v);
+          tmem_ld32(lane_addr + c * 32, v);
           tmem_ld_wait();
           uint32_t o[16];
 #pragma unroll
@@ -283,22 +202,21 @@ enc_fwd_kernel(const __grid_constant__ EncMaps maps, const EncFwdParams p) {
         tc_fence_after();
         const int L = p.L, hw = L >> 1;
         const int jh = half * hw;                                   // this warp's share of the latent columns
-        const float* bias = bias_u + p.tmem_col[l];
+        const float* bias = bias_u + p.bias_off[l];
         const long long b = b0 + row;
         const bool ok = b < p.B;
         float* latrow = p.lat + a * p.lat_gs + b * p.lat_ld;
         __nv_bfloat16* zrow = p.zin + b * p.zin_ld + a * L;
-        const uint32_t tcol = lane_addr + p.tmem_col[l];
-        for (int jj = 0; jj < hw; jj += 16) {
+        for (int jj = 0; jj < hw; jj += 8) {
           const int j = jh + jj;
-          uint32_t vm[16], vl[16];
-          tmem_ld16(tcol + j, vm);
-          tmem_ld16(tcol + L + j, vl);
+          uint32_t vm[8], vl[8];
+          tmem_ld8(lane_addr + j, vm);
+          tmem_ld8(lane_addr + L + j, vl);
           tmem_ld_wait();
           if (ok) {
-            float mu[16], lv[16];
+            float mu[8], lv[8];
 #pragma unroll
-            for (int k = 0; k < 16; k += 4) {
+            for (int k = 0; k < 8; k += 4) {
               const float4 bm = *reinterpret_cast<const float4*>(bias + j + k);
               const float4 bl = *reinterpret_cast<const float4*>(bias + L + j + k);
               mu[k] = __uint_as_float(vm[k]) + bm.x; mu[k + 1] = __uint_as_float(vm[k + 1]) + bm.y;
@@ -308,34 +226,32 @@ enc_fwd_kernel(const __grid_constant__ EncMaps maps, const EncFwdParams p) {
               *reinterpret_cast<float4*>(latrow + j + k) = make_float4(mu[k], mu[k + 1], mu[k + 2], mu[k + 3]);
               *reinterpret_cast<float4*>(latrow + L + j + k) = make_float4(lv[k], lv[k + 1], lv[k + 2], lv[k + 3]);
             }
-            float z[16];
-            float4 e4[4];                                            // branch hoisted: the four Philox calls interleave
+            float4 e4[2];
             if (p.eps) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) e4[k] = *reinterpret_cast<const float4*>(p.eps + b * p.eps_ld + a * L + j + 4 * k);
+              for (int k = 0; k < 2; ++k) e4[k] = *reinterpret_cast<const float4*>(p.eps + b * p.eps_ld + a * L + j + 4 * k);
             } else {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
+              for (int k = 0; k < 2; ++k)
                 e4[k] = philox_normal4(p.seed, p.step, static_cast<uint64_t>(p.sample0 + b), static_cast<uint32_t>((a * L + j + 4 * k) >> 2));
             }
+            float z[8];
 #pragma unroll
-            for (int k = 0; k < 16; k += 4) {
+            for (int k = 0; k < 8; k += 4) {
               const float ev[4] = {e4[k >> 2].x, e4[k >> 2].y, e4[k >> 2].z, e4[k >> 2].w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float s = expf(0.5f * lv[k + i]);
-                z[k + i] = mu[k + i] + ev[i] * s;
-                kl_acc += 1.f + lv[k + i] - mu[k + i] * mu[k + i] - s * s;
+                const float sd = expf(0.5f * lv[k + i]);
+                z[k + i] = mu[k + i] + ev[i] * sd;
+                kl_acc += 1.f + lv[k + i] - mu[k + i] * mu[k + i] - sd * sd;
               }
             }
-            uint32_t pz[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) pz[k] = pack_bf16x2(z[2 * k], z[2 * k + 1], false);
-            *reinterpret_cast<uint4*>(zrow + j) = make_uint4(pz[0], pz[1], pz[2], pz[3]);
-            *reinterpret_cast<uint4*>(zrow + j + 8) = make_uint4(pz[4], pz[5], pz[6], pz[7]);
+            *reinterpret_cast<uint4*>(zrow + j) = make_uint4(pack_bf16x2(z[0], z[1], false), pack_bf16x2(z[2], z[3], false),
+                                                             pack_bf16x2(z[4], z[5], false), pack_bf16x2(z[6], z[7], false));
           }
         }
         tc_fence_before();
+        mbar_arrive(tmem_free);
       }
     }
   }
@@ -356,21 +272,26 @@ struct EncFusedPlan {
   size_t fwd_smem = 0;
 };
 
+static size_t enc_smem_bytes(const EncFusedDesc& d, uint32_t* w_buf_out) {
+  uint32_t wbuf = 0; int cols = 0;
+  for (int l = 0; l < d.nl; ++l) {
+    const int K = (l == 0) ? d.K0 : d.N[l - 1];
+    wbuf = std::max<uint32_t>(wbuf, static_cast<uint32_t>((K + 63) / 64) * d.N[l] * 128);
+    cols += d.N[l];
+  }
+  if (w_buf_out) *w_buf_out = wbuf;
+  return static_cast<size_t>(kActBoxes) * kBoxBytes + wbuf + 256 + 2 * cols * sizeof(float) + 1024;
+}
+
 bool enc_fused_applicable(const EncFusedDesc& d) {
   if (d.nl < 2 || d.nl > kEncMaxL) return false;
-  if (d.K0p > 64 * kActBoxes || d.I % 8 != 0 || d.L % 32 != 0 || 2 * d.L > 256) return false;
-  int cols = 0;
-  size_t wbytes = 0;
+  if (d.K0 > 64 * kActBoxes || d.K0 % 8 != 0 || d.L % 16 != 0 || 2 * d.L > 256) return false;
   for (int l = 0; l < d.nl; ++l) {
-    const int N = d.N[l], K = (l == 0) ? d.K0p : d.N[l - 1];
-    if (N % 16 != 0 || N > 256) return false;
+    const int N = d.N[l];
+    if (N % 16 != 0 || N > kEncTmemCols) return false;
     if (l + 1 < d.nl && N % 64 != 0) return false;
-    cols += N;
-    wbytes += static_cast<size_t>((K + 63) / 64) * N * 128;
   }
-  if (cols > kEncTmemCols) return false;
-  if (kActBoxes * kBoxBytes + wbytes + 256 + 2 * cols * sizeof(float) + 1024 > kEncSmemLimit) return false;
-  return true;
+  return enc_smem_bytes(d, nullptr) <= 227 * 1024 - 2048;
 }
 
 int enc_fused_plan(const EncFusedDesc& d, EncFusedPlan** out) {
@@ -379,21 +300,23 @@ int enc_fused_plan(const EncFusedDesc& d, EncFusedPlan** out) {
   EncFwdParams& p = pl->fp;
   memset(&p, 0, sizeof(p));
   p.A = d.A; p.B = d.B; p.tiles = (d.B + kEncRows - 1) / kEncRows; p.total_units = p.A * p.tiles; p.nl = d.nl;
-  int col = 0; uint32_t woff = 0;
+  int col = 0;
   int rc = 0;
   for (int l = 0; l < d.nl && rc == 0; ++l) {
-    const int N = d.N[l], K = (l == 0) ? d.K0p : d.N[l - 1];
-    p.N[l] = N; p.kboxes[l] = (K + 63) / 64; p.ksteps[l] = (K + 15) / 16; p.tmem_col[l] = col; col += N;
-    p.w_off[l] = woff; woff += static_cast<uint32_t>(p.kboxes[l]) * N * 128;
+    const int N = d.N[l], K = (l == 0) ? d.K0 : d.N[l - 1];
+    p.N[l] = N; p.kboxes[l] = (K + 63) / 64; p.ksteps[l] = (K + 15) / 16;
+    p.w_bytes[l] = static_cast<uint32_t>(p.kboxes[l]) * N * 128;
+    p.bias_off[l] = col; col += N;
     p.bias[l] = d.bias[l];
-    rc = encode_tmap_bf16_3d(&pl->fmaps.w[l], d.W[l], K, N, d.A, K, static_cast<int64_t>(N) * K, 64, N);
-    p.xout[l] = static_cast<__nv_bfloat16*>(d.X[l]); p.xout_gs[l] = d.x_gs[l]; p.xout_ld[l] = d.x_ld[l]; p.xout_w[l] = K;
+    // weights of layer l: K-major [A][N][w_ld], the K valid columns start at W[l]
+    rc = encode_tmap_bf16_3d(&pl->fmaps.w[l], d.W[l], K, N, d.A, d.w_ld[l], d.w_gs[l], 64, N);
+    // input of layer l in HBM: loaded (l = 0: the staged X0F tile) or stored for the backward pass (l >= 1)
     if (rc == 0) rc = encode_tmap_bf16_3d(&pl->fmaps.x[l], d.X[l], K, d.B, d.A, d.x_ld[l], d.x_gs[l], 64, kEncRows);
-    // activation boxes: X0 starts at box 0; a hidden activation goes next to the tile whose TMA store may still be in
-    // flight when it is written, or back to box 0 (then the control thread drains that store first)
+    // activation boxes: X0F starts at box 0; a hidden activation goes next to the tile whose TMA store may still be in
+    // flight when it is written, or back to box 0 (then the control thread drains the pending stores first)
     if (l == 0) p.in_box[0] = 0;
     if (l + 1 < d.nl) {
-      const int in_end = p.in_box[l] + p.kboxes[l];                         // boxes a pending store may be reading
+      const int in_end = p.in_box[l] + p.kboxes[l];
       const int nb_out = N / 64;
       if (in_end + nb_out <= kActBoxes) { p.in_box[l + 1] = in_end; p.wait_store[l] = 0; }
       else { p.in_box[l + 1] = 0; p.wait_store[l] = 1; }
@@ -402,12 +325,12 @@ int enc_fused_plan(const EncFusedDesc& d, EncFusedPlan** out) {
     }
   }
   if (rc != 0) { delete pl; return rc; }
-  p.w_bytes = woff; p.bias_n = col;
-  p.obs_off = d.obs_off; p.obs_dim = d.obs_dim; p.idx_emb = d.idx_emb; p.I = d.I;
+  p.bias_n = col;
   p.lat = d.lat; p.lat_gs = d.lat_gs; p.lat_ld = d.lat_ld;
   p.zin = static_cast<__nv_bfloat16*>(d.zin); p.zin_ld = d.zin_ld; p.L = d.L;
-  pl->grid = std::min(p.total_units, kNumSMs);
-  pl->fwd_smem = static_cast<size_t>(kActBoxes) * kBoxBytes + woff + 256 + 2 * col * sizeof(float) + 1024;
+  pl->fwd_smem = enc_smem_bytes(d, &p.w_buf);
+  const int per_sm = pl->fwd_smem <= kEncSmemLimit ? 2 : 1;
+  pl->grid = std::min(p.total_units, kNumSMs * per_sm);
   *out = pl;
   return 0;
 }
@@ -422,7 +345,6 @@ int enc_fused_forward(EncFusedPlan* pl, const EncFwdBatch& b, cudaStream_t s) {
     attr_bytes = pl->fwd_smem;
   }
   EncFwdParams p = pl->fp;
-  p.obs = b.obs; p.obs_ld = b.obs_ld; p.idx = b.idx; p.idx_ld = b.idx_ld;
   p.eps = b.eps; p.eps_ld = b.eps_ld; p.seed = b.seed; p.step = b.step; p.sample0 = b.sample0;
   p.kl_scale = b.kl_scale; p.kl_out = b.kl_out; p.scratch = b.scratch;
   enc_fwd_kernel<<<pl->grid, kEncThreads, pl->fwd_smem, s>>>(pl->fmaps, p);

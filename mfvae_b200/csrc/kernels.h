@@ -161,18 +161,17 @@ int gemm_tc_loss_partials(const TcPlan* p);               // true: C is fully wr
 // ---- fused per-agent encoder (enc_fused.cu) ---------------------------------------------------
 constexpr int kEncMaxL = 4;
 struct EncFusedDesc {                          // everything that is fixed once arenas + workspace are bound
-  int A = 0, B = 0, nl = 0, I = 0, L = 0, K0p = 0;
+  int A = 0, B = 0, nl = 0, L = 0, K0 = 0;     // K0 = width of the staged input [obs | 0] (the id-embedding is folded into bias[0])
   int N[kEncMaxL] = {0, 0, 0, 0};              // output width of layer l (last = 2L)
-  const void* W[kEncMaxL] = {};                // bf16 [A][N_l][K_l]
+  const void* W[kEncMaxL] = {};                // bf16, first valid column of layer l's weights: element (a, n, k) at W + a*w_gs + n*w_ld + k
+  int64_t w_ld[kEncMaxL] = {}, w_gs[kEncMaxL] = {};
   const float* bias[kEncMaxL] = {};            // fp32 [A][N_l]
-  void* X[kEncMaxL] = {};                      // bf16 input of layer l, [A][B][x_ld]: X0, XE_0, ...
+  void* X[kEncMaxL] = {};                      // bf16 input of layer l, [A][B][x_ld]: X0F (read), XE_0, ... (written)
   int64_t x_ld[kEncMaxL] = {}, x_gs[kEncMaxL] = {};
-  const float* idx_emb = nullptr; const int32_t* obs_off = nullptr; const int32_t* obs_dim = nullptr;
   float* lat = nullptr; int64_t lat_gs = 0, lat_ld = 0;
   void* zin = nullptr; int64_t zin_ld = 0;
 };
 struct EncFwdBatch {
-  const float* obs; int64_t obs_ld; const float* idx; int idx_ld;
   const float* eps; int64_t eps_ld; uint64_t seed, step; int64_t sample0;
   float kl_scale; float* kl_out; float* scratch;
 };

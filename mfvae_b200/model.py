@@ -267,6 +267,8 @@ class MAVAE(nn.Module):
         cfg.optimize_encoders = int(self.optimize_encoders)
         cfg.continuous_act = 0 if descrete_act else 1
         cfg.act_hidden = ActionEncoder.HIDDEN[0]
+        if fusion == "auto":          # measurement knob: MFVAE_FUSION overrides what "auto" resolves to
+            fusion = _os.environ.get("MFVAE_FUSION", "auto")
         cfg.fusion = {"auto": L.FUSE_AUTO, "none": L.FUSE_NONE, "encoder": L.FUSE_ENCODER, "loss": L.FUSE_LOSS,
                       "encoder+loss": L.FUSE_ENCODER | L.FUSE_LOSS, "nofold": L.FUSE_NONE | L.FUSE_NOFOLD_IDX | L.FUSE_NOFOLD_ACT, "nofold_idx": L.FUSE_NONE | L.FUSE_NOFOLD_IDX,
                       "nofold_act": L.FUSE_NONE | L.FUSE_NOFOLD_ACT}[fusion]

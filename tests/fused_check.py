@@ -24,12 +24,10 @@ def main(latent, B, explicit_idx=False):
     dev = "cuda:0"
     spec = O.simple_tag_spec(latent=latent)
     models = {}
-    # baseline "none" = per-layer kernels with the id-embedding columns kept dense ("nofold_idx"): the fused encoder kernel
-    # stages those columns itself, so both sides share every bf16 rounding point
     for fusion in ("none", "encoder", "loss"):
         torch.manual_seed(7)
         m = M.MAVAE(spec.idx_features, spec.latent, spec.act_features, True, spec.agents, spec.obs_dim, spec.n_act, dev,
-                    precision="bf16", fusion="nofold_idx" if fusion == "none" else fusion, include_dead_decoder=False)
+                    precision="bf16", fusion=fusion, include_dead_decoder=False)
         models[fusion] = m
     for k in ("encoder", "loss"):
         models[k].load_named(models["none"].named_arena_tensors())

@@ -134,7 +134,7 @@ def main(case, precision, engine, mode="dropin", rng="eps", fusion="auto", flags
             # fast path = fwd+loss+bwd+adam in one call; compare losses and the post-step parameters only
             Gq = None
             if step == 0 and precision == "bf16":      # gradients of the fused step against the bf16-emulating oracle
-                _, Gq, _ = O.grads(st.P, spec, idx_state, acts, eps, nxt, rew, huber, emulate_bf16=True, fold_idx=("encoder" not in fusion))
+                _, Gq, _ = O.grads(st.P, spec, idx_state, acts, eps, nxt, rew, huber, emulate_bf16=True)
             P0 = {k: v.clone() for k, v in st.P.items()}
             losses_dev = m.train_step(pb, lr)
             sched.step()
@@ -197,7 +197,7 @@ def main(case, precision, engine, mode="dropin", rng="eps", fusion="auto", flags
                 if precision == "bf16" and mode != "jointmse":
                     # the same algorithm with the CUDA path's bf16 rounding points (oracle emulate_bf16): isolates kernel
                     # errors from the ReLU-mask flips any bf16 evaluation shows against an fp32 run
-                    _, Gq, outs_q = O.grads(st.P, spec, idx_state, acts, eps, nxt, rew, huber, emulate_bf16=True, fold_idx=("encoder" not in fusion))
+                    _, Gq, outs_q = O.grads(st.P, spec, idx_state, acts, eps, nxt, rew, huber, emulate_bf16=True)
                     qerr = {k: rel_l2(p.grad, Gq[k]) for k, p in mine.items()}
                     qw = max(qerr, key=qerr.get)
                     out["grad_rel_max_vs_bf16_oracle"] = qerr[qw]; out["grad_rel_worst_vs_bf16_oracle"] = qw

@@ -490,22 +490,28 @@ def run_ours(args, w):
         for (kind, G, Mm, Nn, Kk, j), v in acc.items():
             msj = float(np.mean(v)); fl = 2.0 * G * Mm * Nn * Kk
             tot_ms += msj; tot_fl += fl
-            rows.append({"kind": ["fwd", "dgrad", "wgrad"][kind], "G": G, "M": Mm, "N": Nn, "K": Kk, "ms": round(msj, 4),
-                         "tflops": round(fl / (msj * 1e-3) / 1e12, 1) if msj > 0 else None})
+            rows.append({"kind": ["fwd", "dgrad", "wgrad", "fused encoder chain (fwd, 4 layers + reparam + KL)"][kind], "G": G, "M": Mm, "N": Nn, "K": Kk,
+                         "ms": round(msj, 4), "tflops": round(fl / (msj * 1e-3) / 1e12, 1) if msj > 0 else None})
         rows.sort(key=lambda r: -r["ms"])
         if tot_ms > 0:
             ach = tot_fl / (tot_ms * 1e-3) / 1e12
+            # the same launches against the REFERENCE's dense flop count (6 flops per MAC of its nn.Linear layers):
+            # the folded column blocks (csrc/fold.cu) do the same mathematics with 30 % fewer executed flops
+            alg_fl = float(flops_per_sample(spec)) * B
+            alg = alg_fl / (tot_ms * 1e-3) / 1e12
             bound = "tensor" if w["precision"] == "bf16" else "fp32-simt"
             # DRAM traffic of the same launches: dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu launch list
-            # (profiles/r1_traffic.json); only valid for the workload / batch it was captured on
+            # (profiles/r2_traffic.json); only valid for the workload / batch it was captured on
             traffic = None
-            tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+            tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
             if args.workload == "cfg2" and B == 4096 and os.path.exists(tp):
-                traffic = json.load(open(tp))["cfg2_b4096"]["gemm_tc_kernel_all_launches"]["dram_bytes_per_step"]
+                traffic = json.load(open(tp))["cfg2_b4096"]["tensor_core_kernels_all_launches"]["dram_bytes_per_step"]
             roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                    "traffic": traffic, "traffic_note": "bytes per step over the same 36 launches (ncu, profiles/r1_traffic.json)",
-                    "kernel": "gemm_tc_kernel (all %d GEMM launches of one step)" % len(rows),
-                    "gemm_ms_per_step": tot_ms, "gemm_flop_per_step": tot_fl, "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
+                    "achieved_vs_reference_flop_count": alg, "frac_vs_reference_flop_count": alg / pk["tf_sustained"],
+                    "traffic": traffic, "traffic_note": "bytes per step over the same launches (ncu, profiles/r2_traffic.json)",
+                    "kernel": "gemm_tc_kernel + enc_fwd_kernel (all %d tensor-core launches of one step)" % len(rows),
+                    "gemm_ms_per_step": tot_ms, "gemm_flop_per_step": tot_fl, "reference_flop_per_step": alg_fl,
+                    "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
                     "engine": bound, "top": rows[:8], "all": rows}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on this box's host cores, bounded sample ----

@@ -191,7 +191,8 @@ int mfvae_fwd_bwd(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* s
 /* instrumentation: number of kernels this library has launched so far (process-wide), and optional CUDA-event
  * timing of every GEMM launch of the step on its launching stream.  With profiling on, each step records
  * start/stop events around its GEMM launches; mfvae_profile_read synchronises and returns, per GEMM of the last
- * step, {M, N, K, groups, kind (0 fwd, 1 dgrad, 2 wgrad), milliseconds}. */
+ * step, {M, N, K, groups, kind (0 fwd, 1 dgrad, 2 wgrad, 3 = the fused encoder chain: N = 1, K = MACs per (agent, sample)),
+ * milliseconds}. */
 uint64_t mfvae_launch_count(void);
 typedef struct MfvaeGemmTiming { int32_t M, N, K, groups, kind; float ms; } MfvaeGemmTiming;
 int mfvae_profile_enable(MfvaeHandle h, int32_t on);
@@ -258,18 +259,21 @@ int mfvae_gemm(int32_t engine, int32_t dtype, int32_t groups, int32_t M, int32_t
                const void* d_aux, int64_t aux_gs, int64_t aux_ld, int32_t split_k, void* stream);
 
 /* HBM-resident replay ring (replaces cpprb.ReplayBuffer / flashbax item buffer on this path).
- * Row = one joint transition: [obs(S) | act(A) | next(S) | rew(A) | done(1)] fp32. */
+ * Row = one joint transition with every key of the reference's cpprb env_dict (torch_ver/src/replay_buffer.py:62-81):
+ *   [obs(S) | act(W) | next(S) | rew(A) | terminals(A) | truncations(A) | mask(1)] fp32,
+ * W = act_cols = A for float-coded discrete actions, sum of the agents' action widths for continuous actions. */
 typedef struct MfvaeRing_* MfvaeRing;
-int mfvae_ring_create(int32_t state_dim, int32_t n_agents, int64_t capacity, float* d_storage, MfvaeRing* out);
+int mfvae_ring_create(int32_t state_dim, int32_t n_agents, int32_t act_cols, int64_t capacity, float* d_storage, MfvaeRing* out);
 int mfvae_ring_destroy(MfvaeRing r);
-int64_t mfvae_ring_row_floats(int32_t state_dim, int32_t n_agents);
+int64_t mfvae_ring_row_floats(int32_t state_dim, int32_t n_agents, int32_t act_cols);
 int64_t mfvae_ring_size(MfvaeRing r);
 /* append n rows from a host or device staging buffer (cudaMemcpyAsync, wraps around) */
 int mfvae_ring_add(MfvaeRing r, const float* rows, int64_t n, int32_t rows_on_device, void* stream);
-/* uniform-with-replacement sample (Philox(seed, step)) and gather into the packed batch matrices */
+/* uniform-with-replacement sample (Philox(seed, step)) and gather into the packed batch matrices; d_flags_or_null
+ * [batch, 2 A + 1] receives terminals | truncations | mask of the sampled rows */
 int mfvae_ring_sample(MfvaeRing r, int64_t batch, uint64_t seed, uint64_t step,
-                      float* d_obs, float* d_act, float* d_next, float* d_rew, int32_t* d_indices_or_null,
-                      void* stream);
+                      float* d_obs, float* d_act, float* d_next, float* d_rew, float* d_flags_or_null,
+                      int32_t* d_indices_or_null, void* stream);
 
 #ifdef __cplusplus
 }

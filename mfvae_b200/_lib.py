@@ -101,12 +101,12 @@ SIGNATURES = {
     "mfvae_philox_normal": (C.c_int, [_vp, _i64, _i32, _u64, _u64, _i64, _vp]),
     "mfvae_gemm": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
                              _vp, _i64, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i64, _i32, _vp]),
-    "mfvae_ring_create": (C.c_int, [_i32, _i32, _i64, _vp, C.POINTER(_vp)]),
+    "mfvae_ring_create": (C.c_int, [_i32, _i32, _i32, _i64, _vp, C.POINTER(_vp)]),
     "mfvae_ring_destroy": (C.c_int, [_vp]),
-    "mfvae_ring_row_floats": (_i64, [_i32, _i32]),
+    "mfvae_ring_row_floats": (_i64, [_i32, _i32, _i32]),
     "mfvae_ring_size": (_i64, [_vp]),
     "mfvae_ring_add": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
-    "mfvae_ring_sample": (C.c_int, [_vp, _i64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mfvae_ring_sample": (C.c_int, [_vp, _i64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -108,6 +108,7 @@ struct MfvaeHandle_ {
   bool profiling = false;
   std::vector<cudaEvent_t> prof_ev;          // 2 per GEMM op
   std::vector<char> prof_hit;
+  cudaEvent_t enc_prof_ev[2] = {nullptr, nullptr}; bool enc_prof_hit = false;   // the fused encoder chain, timed as one item
 
   std::vector<cudaEvent_t> ar_ev = std::vector<cudaEvent_t>(8, nullptr); size_t ar_ev_i = 0;   // reduce -> optimizer-stream hand-off
   CommCtx comm;                              // data-parallel exchange over peer memory (mfvae_comm_bind); world == 1: unbound
@@ -595,12 +596,14 @@ static int do_forward(MfvaeHandle_* h, const MfvaeBatch* b, MfvaeOutputs* out, c
   }
   MFVAE_TRY(launch_stage(st, s, true, false));
   if (fold_i && use_aux(h)) MFVAE_CUDA(cudaStreamWaitEvent(s, h->eb_ev, 0));
-  if (fold_i && h->enc_fused && !h->profiling) {
+  if (fold_i && h->enc_fused) {
     // the four encoder layers, reparameterisation and KL as ONE kernel (enc_fused.cu) on the staged tile
     EncFwdBatch eb{};
     eb.eps = b->d_eps; eb.eps_ld = static_cast<int64_t>(h->A) * h->L; eb.seed = b->seed; eb.step = b->step; eb.sample0 = b->sample0;
     eb.kl_scale = 1.0f / static_cast<float>(b->batch_global); eb.kl_out = losses_ptr(h) + 3; eb.scratch = scratch_ptr(h, 0);
+    if (h->profiling && h->enc_prof_ev[0]) MFVAE_CUDA(cudaEventRecord(h->enc_prof_ev[0], s));
     MFVAE_TRY(enc_fused_forward(h->enc_fused, eb, s));
+    if (h->profiling && h->enc_prof_ev[0]) { MFVAE_CUDA(cudaEventRecord(h->enc_prof_ev[1], s)); h->enc_prof_hit = true; }
     return do_forward_decoders(h, s, lb, h->cfg.huber, recon16, defer_reward_join);
   }
   MFVAE_TRY(run_gemm(h, fold_i ? h->g_enc_fwd0_f : h->g_enc_fwd[0], s));
@@ -929,6 +932,7 @@ int mfvae_destroy(MfvaeHandle h) {
   free_plans(h);
   for (auto& b : h->buckets) if (b.ev) cudaEventDestroy(b.ev);
   for (auto e : h->prof_ev) cudaEventDestroy(e);
+  for (auto e : h->enc_prof_ev) if (e) cudaEventDestroy(e);
   for (auto e : h->fork_ev) if (e) cudaEventDestroy(e);
   if (h->join_ev) cudaEventDestroy(h->join_ev);
   if (h->side) cudaStreamDestroy(h->side);
@@ -1219,6 +1223,8 @@ int mfvae_profile_enable(MfvaeHandle h, int32_t on) {
       cudaEvent_t e; MFVAE_CUDA(cudaEventCreate(&e)); h->prof_ev.push_back(e);
     }
     h->prof_hit.assign(h->gemms.size(), 0);
+    for (auto& e : h->enc_prof_ev) if (!e) MFVAE_CUDA(cudaEventCreate(&e));
+    h->enc_prof_hit = false;
   }
   h->profiling = on != 0;
   return 0;
@@ -1235,6 +1241,17 @@ int32_t mfvae_profile_read(MfvaeHandle h, MfvaeGemmTiming* out, int32_t capacity
     const GemmOp& o = h->gemms[i];
     const int kind = (o.epi == kEpiAccum) ? 2 : ((o.b_rs == 1 && o.b_cs != 1) ? 1 : 0);
     out[n++] = MfvaeGemmTiming{o.M, o.N, o.K, o.G, kind, ms};
+  }
+  if (h->enc_prof_hit && n < capacity) {
+    // the fused encoder chain as one item: kind 3, groups = agents, M = batch, N = 1, K = MACs per (agent, sample) of the chain,
+    // so that 2 * groups * M * N * K is its flop count like every other row
+    if (cudaEventSynchronize(h->enc_prof_ev[1]) != cudaSuccess) return -1;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->enc_prof_ev[0], h->enc_prof_ev[1]) != cudaSuccess) return -1;
+    int macs = 0;
+    for (int l = 0; l < h->ne; ++l) macs += ((l == 0) ? h->K0f : h->encK[l]) * h->encN[l];
+    out[n++] = MfvaeGemmTiming{h->B, 1, macs, h->A, 3, ms};
+    h->enc_prof_hit = false;
   }
   return n;
 }

@@ -113,10 +113,10 @@ def test_simt_gemm_all_majors_and_epilogues(lib, dtype):
 
 def test_ring_sample_gathers_rows(lib):
     S, A, cap = 24, 4, 50
-    row = lib.lib().mfvae_ring_row_floats(S, A)
+    row = lib.lib().mfvae_ring_row_floats(S, A, A)
     storage = torch.zeros(cap * row, device="cuda")
     r = C.c_void_p()
-    lib.check(lib.lib().mfvae_ring_create(S, A, cap, lib.ptr(storage), C.byref(r)))
+    lib.check(lib.lib().mfvae_ring_create(S, A, A, cap, lib.ptr(storage), C.byref(r)))
     host = torch.arange(70 * row, dtype=torch.float32).reshape(70, row)      # 70 rows into a 50-slot ring: wraps
     lib.check(lib.lib().mfvae_ring_add(r, C.c_void_p(host.data_ptr()), 30, 0, _stream()))
     lib.check(lib.lib().mfvae_ring_add(r, C.c_void_p(host[30:].data_ptr()), 40, 0, _stream()))
@@ -126,13 +126,15 @@ def test_ring_sample_gathers_rows(lib):
     obs = torch.empty(B, S, device="cuda"); nxt = torch.empty(B, S, device="cuda")
     act = torch.empty(B, A, device="cuda"); rew = torch.empty(B, A, device="cuda")
     idx = torch.empty(B, dtype=torch.int32, device="cuda")
-    lib.check(lib.lib().mfvae_ring_sample(r, B, 9, 1, lib.ptr(obs), lib.ptr(act), lib.ptr(nxt), lib.ptr(rew), lib.ptr(idx), _stream()))
+    flags = torch.empty(B, 2 * A + 1, device="cuda")
+    lib.check(lib.lib().mfvae_ring_sample(r, B, 9, 1, lib.ptr(obs), lib.ptr(act), lib.ptr(nxt), lib.ptr(rew), lib.ptr(flags), lib.ptr(idx), _stream()))
     torch.cuda.synchronize()
     st = storage.view(cap, row)
     ii = idx.long()
     assert int(ii.min()) >= 0 and int(ii.max()) < 50 and len(set(ii.tolist())) > 20
     assert torch.equal(obs, st[ii, :S]) and torch.equal(act, st[ii, S:S + A])
     assert torch.equal(nxt, st[ii, S + A:2 * S + A]) and torch.equal(rew, st[ii, 2 * S + A:2 * S + 2 * A])
+    assert torch.equal(flags, st[ii, 2 * S + 2 * A:2 * S + 4 * A + 1])          # terminals | truncations | mask
     # slots 0..19 were overwritten by rows 50..69 (ring semantics of cpprb / flashbax)
     assert torch.equal(st[:20].cpu(), host[50:70]) and torch.equal(st[20:30].cpu(), host[20:30])
     lib.lib().mfvae_ring_destroy(r)
@@ -168,7 +170,7 @@ def test_replay_wrappers_match_reference_contracts(lib):
         nxt = {a: rng.standard_normal(spec.obs_dim[a]).astype(np.float32) for a in spec.agents}
         act = {a: int(rng.integers(0, 5)) for a in spec.agents}
         rew = {a: float(rng.standard_normal()) for a in spec.agents}
-        term = {a: False for a in spec.agents}; trunc = {a: t % 25 == 24 for a in spec.agents}
+        term = {a: (t % 7 == 3 and a == spec.agents[0]) for a in spec.agents}; trunc = {a: t % 25 == 24 for a in spec.agents}
         buf.add(obs, nxt, act, rew, term, trunc)
         rows.append(np.concatenate([obs[a] for a in spec.agents]))
         if t % 25 == 24:
@@ -181,8 +183,12 @@ def test_replay_wrappers_match_reference_contracts(lib):
         assert d[f"{a}_actions"].shape == (16, 1) and d[f"{a}_rewards"].shape == (16, 1)
     stored = np.stack(rows[15:])                                        # the 40 newest survive
     got = np.concatenate([d[f"{a}_observations"] for a in spec.agents], axis=1)
-    for r in got:
-        assert np.any(np.all(np.isclose(stored, r[None, :]), axis=1))
+    for k, r in enumerate(got):
+        hit = np.flatnonzero(np.all(np.isclose(stored, r[None, :]), axis=1))
+        assert hit.size == 1
+        t = 15 + int(hit[0])                                            # the step this row was added at: per-agent flags as added
+        assert d[f"{spec.agents[0]}_terminals"][k, 0] == float(t % 7 == 3) and d[f"{spec.agents[1]}_terminals"][k, 0] == 0.0
+        assert all(d[f"{a}_truncations"][k, 0] == float(t % 25 == 24) for a in spec.agents) and d["mask"][k, 0] == 0.0
     idx_state, acts, joint, nxt_t, rew_t = M.create_dataset(d, {a: i for i, a in enumerate(spec.agents)})
     assert nxt_t.shape == (16, spec.state_dim) and idx_state[spec.agents[0]].shape == (16, 1 + spec.obs_dim[spec.agents[0]])
     pb = buf.sample_packed()
@@ -199,4 +205,19 @@ def test_replay_wrappers_match_reference_contracts(lib):
     assert set(e) == {f"{a}_{k}" for a in spec.agents for k in ("obs", "act", "next_obs", "rew")} | {"done"}
     a0 = spec.agents[0]
     assert e[f"{a0}_obs"].shape == (4, spec.obs_dim[a0], 1) and e[f"{a0}_act"].shape == (4, 1, 1) and e["done"].shape == (4, 1, 1)
-    assert np.allclose(e[f"{a0}_obs"][:, :, 0], o[a0][None, :]) and np.all(e[f"{a0}_act"] == 2)
+    assert np.allclose(e[f"{a0}_obs"][:, :, 0], o[a0][None, :]) and np.all(e[f"{a0}_act"] == 2) and np.all(e["done"] == 0.0)
+
+    # continuous actions (Box action spaces): the ring keeps whole action vectors, sample() hands them back per agent
+    act_dim = {a: (5 if i < 2 else 3) for i, a in enumerate(spec.agents)}
+    cb = M.MultiAgentCPPRB(max_size=16, batch_size=8, agents=spec.agents, obs_dim=spec.obs_dim, act_dim=act_dim)
+    acts_added = []
+    for t in range(10):
+        act = {a: rng.uniform(0, 1, act_dim[a]).astype(np.float32) for a in spec.agents}
+        cb.add(o, o, act, {a: 0.5 for a in o}, {a: False for a in o}, {a: False for a in o})
+        acts_added.append(np.concatenate([act[a] for a in spec.agents]))
+    dc = cb.sample()
+    assert all(dc[f"{a}_actions"].shape == (8, act_dim[a]) for a in spec.agents)
+    got = np.concatenate([dc[f"{a}_actions"] for a in spec.agents], axis=1)
+    for r in got:
+        assert np.any(np.all(np.isclose(np.stack(acts_added), r[None, :]), axis=1))
+    assert cb.sample_packed().act.shape == (8, sum(act_dim.values()))

@@ -59,14 +59,15 @@ template <typename T>
 __global__ void __launch_bounds__(kFoldThreads) act_fold_fwd_kernel(const float* __restrict__ W0, int64_t w_ld, int wcol0,
                                                                     const float* __restrict__ table, int64_t table_gs,
                                                                     T* __restrict__ Tt, int64_t t_ld, int rows, int A, int C, int nmax) {
-  extern __shared__ float wrow[];                      // [kRowsF][A*C]
-  const int AC = A * C;
+  extern __shared__ float wrow[];                      // [kRowsF][A][C + 4]: the agent pitch is padded by one 16-byte chunk, so the
+  const int AC = A * C, CP = C + 4, ACP = A * CP;      // lanes of a warp (5 k's of ~7 agents each) read distinct banks
   const int h0 = blockIdx.x * kRowsF;
   for (int i = threadIdx.x; i < kRowsF * (AC / 4); i += blockDim.x) {
     const int r = i / (AC / 4), q = i - r * (AC / 4);
+    const int a = (q * 4) / C, c = q * 4 - a * C;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (h0 + r < rows) v = ldg_stream4(W0 + static_cast<int64_t>(h0 + r) * w_ld + wcol0 + q * 4);
-    reinterpret_cast<float4*>(wrow)[i] = v;
+    *reinterpret_cast<float4*>(wrow + r * ACP + a * CP + c) = v;
   }
   __syncthreads();
   for (int j = threadIdx.x; j < t_ld; j += blockDim.x) {
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(kFoldThreads) act_fold_fwd_kernel(const float*
         const float4 t = __ldg(tb + c4);
 #pragma unroll
         for (int r = 0; r < kRowsF; ++r) {
-          const float4 w = reinterpret_cast<const float4*>(wrow + r * AC + a * C)[c4];
+          const float4 w = reinterpret_cast<const float4*>(wrow + r * ACP + a * CP)[c4];
           acc[r] = fmaf(w.x, t.x, fmaf(w.y, t.y, fmaf(w.z, t.z, fmaf(w.w, t.w, acc[r]))));
         }
       }
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(kFoldThreads) act_fold_fwd_kernel(const float*
 int launch_act_fold_fwd(const float* W0, int64_t w_ld, int wcol0, const float* table, int64_t table_gs, void* Tt, int dtype, int64_t t_ld,
                         int rows, int A, int C, int nmax, cudaStream_t s) {
   MFVAE_CHECK(C % 4 == 0 && w_ld % 4 == 0 && wcol0 % 4 == 0 && table_gs % 4 == 0, "act fold: widths must be multiples of 4");
-  const size_t smem = static_cast<size_t>(kRowsF) * A * C * sizeof(float);
+  const size_t smem = static_cast<size_t>(kRowsF) * A * (C + 4) * sizeof(float);
   MFVAE_CHECK(smem <= 160 * 1024, "act fold: A * act_features too large for the shared-memory row buffer");
   const int grid = (rows + kRowsF - 1) / kRowsF;
   if (dtype == kBF16) {
@@ -114,12 +115,11 @@ int launch_act_fold_fwd(const float* W0, int64_t w_ld, int wcol0, const float* t
 //   gW0[h][wcol0 + a*C + c]  = sum_k dT[h][a*nmax + k] * table[a][k][c]        (plain store: these columns have no other writer)
 //   gtable[a][k][c]         += sum_h dT[h][a*nmax + k] * W0[h][wcol0 + a*C + c] (atomics into the zeroed gradient arena)
 // grid = (row chunks of kRowsB, A); a thread owns 4 consecutive columns c (16-byte accesses) and walks the chunk's rows.
-constexpr int kRowsB = 128;
 template <int NMAX>
 __global__ void __launch_bounds__(kFoldThreads) act_fold_bwd_kernel(const float* __restrict__ dT, int64_t t_ld, const float* __restrict__ W0,
                                                                     float* __restrict__ gW0, int64_t w_ld, int wcol0,
                                                                     const float* __restrict__ table, float* __restrict__ gtable, int64_t table_gs,
-                                                                    int rows, int C, int nmax) {
+                                                                    int rows, int C, int nmax, int rows_per_cta) {
   __shared__ float4 fold[kFoldThreads];
   const int a = blockIdx.y;
   const int strips = C / 4;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kFoldThreads) act_fold_bwd_kernel(const float*
     tab[k] = (k < nmax) ? __ldg(reinterpret_cast<const float4*>(table + a * table_gs + static_cast<int64_t>(k) * C) + strip) : make_float4(0.f, 0.f, 0.f, 0.f);
     acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  const int h0 = blockIdx.x * kRowsB, h1 = min(rows, h0 + kRowsB);
+  const int h0 = blockIdx.x * rows_per_cta, h1 = min(rows, h0 + rows_per_cta);
   if (rphase < nph) {
     for (int h = h0 + rphase; h < h1; h += nph) {
       const float* d = dT + static_cast<int64_t>(h) * t_ld + a * nmax;
@@ -167,9 +167,12 @@ int launch_act_fold_bwd(const float* dT, int64_t t_ld, const float* W0, float* g
                         int64_t table_gs, int rows, int A, int C, int nmax, cudaStream_t s) {
   MFVAE_CHECK(C / 4 <= kFoldThreads && C % 4 == 0 && nmax <= 16 && w_ld % 4 == 0 && wcol0 % 4 == 0 && table_gs % 4 == 0,
               "act fold: act_features % 4 == 0, <= 1024 and n_act <= 16");
-  dim3 grid((rows + kRowsB - 1) / kRowsB, A);
-  if (nmax <= 8) act_fold_bwd_kernel<8><<<grid, kFoldThreads, 0, s>>>(dT, t_ld, W0, gW0, w_ld, wcol0, table, gtable, table_gs, rows, C, nmax);
-  else           act_fold_bwd_kernel<16><<<grid, kFoldThreads, 0, s>>>(dT, t_ld, W0, gW0, w_ld, wcol0, table, gtable, table_gs, rows, C, nmax);
+  // one wave: (row chunks x agents) CTAs <= 148 SMs x 2 resident CTAs of this register footprint (96 registers x 256 threads)
+  const int chunks = std::max(1, std::min(rows, (kNumSMs * 2) / std::max(A, 1)));
+  const int rows_per_cta = (rows + chunks - 1) / chunks;
+  dim3 grid((rows + rows_per_cta - 1) / rows_per_cta, A);
+  if (nmax <= 8) act_fold_bwd_kernel<8><<<grid, kFoldThreads, 0, s>>>(dT, t_ld, W0, gW0, w_ld, wcol0, table, gtable, table_gs, rows, C, nmax, rows_per_cta);
+  else           act_fold_bwd_kernel<16><<<grid, kFoldThreads, 0, s>>>(dT, t_ld, W0, gW0, w_ld, wcol0, table, gtable, table_gs, rows, C, nmax, rows_per_cta);
   MFVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -12,7 +12,7 @@ ncu --set full --clock-control none --import-source on --kernel-name 'regex:^enc
 ncu -i $OUT/enc_fwd.ncu-rep --page raw --csv > $OUT/r2_ncu_full_enc_fwd_raw.csv 2>/dev/null
 ncu -i $OUT/enc_fwd.ncu-rep --page details --csv > $OUT/r2_ncu_full_enc_fwd_details.csv 2>/dev/null
 rm -f $OUT/enc_fwd.ncu-rep
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled --kernel-name 'regex:gemm_tc_kernel<256, true, true, 1>' --launch-skip 6 -c 2 -f -o $OUT/gemm_wg \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled --kernel-name 'regex:gemm_tc_kernel<\(int\)256, \(bool\)1, \(bool\)1' --launch-skip 6 -c 2 -f -o $OUT/gemm_wg \
     python tools/one_step.py --steps 6 > $OUT/ncu_full2.log 2>&1
 ncu -i $OUT/gemm_wg.ncu-rep --page raw --csv > $OUT/r2_ncu_full_gemm_wgrad_raw.csv 2>/dev/null
 ncu -i $OUT/gemm_wg.ncu-rep --page details --csv > $OUT/r2_ncu_full_gemm_wgrad_details.csv 2>/dev/null

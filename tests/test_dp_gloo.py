@@ -24,9 +24,16 @@ def _worker(rank, world, port, q):
     try:
         import mfvae_b200 as M
         spec = O.tiny_spec(3, idx_features=16, latent=8, act_features=8)
+        torch.manual_seed(100 + rank)                       # replicas start DIFFERENT: torch-default init per rank
         m = M.MAVAE(16, 8, 8, True, spec.agents, spec.obs_dim, spec.n_act, "cpu", precision="fp32")
+        m._m.fill_(float(rank)); m._adam_t = 3 + rank; m.philox_step = 10 * (rank + 1)
         m.enable_data_parallel()
         assert m.data_parallel
+        # (0) enable_data_parallel broadcasts rank 0's parameters, Adam moments / step and Philox position
+        ref = m._arena.clone(); dist.broadcast(ref, 0)
+        ok0 = torch.equal(ref, m._arena) and float(m._m.abs().max()) == 0.0 and (m._adam_t, m.philox_step) == (3, 10)
+        # the autograd-bridge path scales its seeds by 1 / world (a torch loss is a LOCAL-batch mean, the exchange a sum)
+        ok0 = ok0 and m._world() == world
         # (1) arena all-reduce over the buckets: every optimised element is summed exactly once
         m._grad.fill_(0.0)
         m._grad[:m._n_opt] = float(rank + 1)
@@ -58,7 +65,7 @@ def _worker(rank, world, port, q):
         flat_full = torch.cat([Gf[k].reshape(-1) for k in sorted(Gf)])
         ok3 = float((flat - flat_full).abs().max()) <= 2e-6 * float(flat_full.abs().max())
         ok3 = ok3 and max(abs(float(a) - b) / abs(b) for a, b in zip(lvec, losses_full)) < 1e-5
-        q.put((rank, ok1, ok2, ok3))
+        q.put((rank, ok0 and ok1, ok2, ok3))
     finally:
         dist.destroy_process_group()
 
@@ -75,6 +82,6 @@ def test_data_parallel_host_logic_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, ok1, ok2, ok3 in res:
-        assert ok1, f"rank {rank}: bucketed all-reduce"
+        assert ok1, f"rank {rank}: state broadcast / bucketed all-reduce"
         assert ok2, f"rank {rank}: Philox shard"
         assert ok3, f"rank {rank}: sharded gradients do not add up to the full-batch gradient"

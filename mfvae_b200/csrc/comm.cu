@@ -124,6 +124,8 @@ struct CommArgs {
 
 // two-shot all-reduce of window bytes [byte0, byte1) (multiples of 16), in place in every window.  With `src` the kernel first
 // packs this rank's fp32 gradients of the range into its window (no separate pack launch waiting for CTA slots).
+// (Capping this kernel at 40 registers so that it fits beside three resident GEMM CTAs of backward's small layers was measured:
+// no change at 2 GPUs -- the data-parallel overhead is not CTA eviction.)
 template <typename TP, bool MC>
 __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommArgs c, int64_t byte0, int64_t byte1, const float* __restrict__ src) {
   if (src) {

@@ -100,10 +100,11 @@ def test_headline_shape_cfg2_b4096_bf16_fast_path():
     bf16 rounding points, and the WHOLE gradient (all tensors concatenated) as relative L2 + cosine against both oracles."""
     o = run("cfg2_b4096", "bf16", "tcgen05", "fast")
     assert o["loss_rel_oracle"][0] < 1e-3, o["loss_rel_oracle"]
-    assert o["grad_rel_median_vs_bf16_oracle"] < 2e-3
-    assert o["grad_rel_max_vs_bf16_oracle"] < 3e-2, o["grad_rel_worst_vs_bf16_oracle"]
-    assert o["whole_grad_rel_vs_bf16_oracle"] < 5e-3 and o["whole_grad_cos_vs_bf16_oracle"] > 0.9999
-    assert o["whole_grad_rel"] < 3e-2 and o["whole_grad_cos"] > 0.999          # vs the fp32 oracle
+    # measured (profiles/r2_parity.jsonl): median 3.2e-5, max 1.1e-2, whole gradient 2.3e-4 (same rounding points); 2.3e-3 vs fp32
+    assert o["grad_rel_median_vs_bf16_oracle"] < 5e-4
+    assert o["grad_rel_max_vs_bf16_oracle"] < 2.5e-2, o["grad_rel_worst_vs_bf16_oracle"]
+    assert o["whole_grad_rel_vs_bf16_oracle"] < 1e-3 and o["whole_grad_cos_vs_bf16_oracle"] > 0.999999
+    assert o["whole_grad_rel"] < 8e-3 and o["whole_grad_cos"] > 0.9999          # vs the fp32 oracle
 
 
 def _fp32_vs_exact(o):

@@ -1158,7 +1158,12 @@ int mfvae_comm_bind(MfvaeHandle h, int32_t rank, int32_t world, void* const* d_p
   // one 32-bit flag per (block, peer) behind the 64 slots left to the host framework
   const int64_t slot_blocks = (signal_pad_bytes / 4 - 64) / world;
   MFVAE_CHECK(slot_blocks >= 1, "comm: signal pads too small (need >= 256 + 4 * world bytes)");
-  c.max_blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(max_blocks > 0 ? max_blocks : 128, slot_blocks), kNumSMs)));
+  // CTAs of a reduce: measured (cfg2, B = 4096 per GPU).  At 2 GPUs a rank moves half of every bucket and needs the bytes in
+  // flight: 128 CTAs (0.985 ms vs 1.04 with 32).  From 4 GPUs the slices are small and the reduce mostly waits in its barriers,
+  // where resident CTAs only take slots from backward's kernels: 32 CTAs (4 GPUs: 0.956 vs 0.997 with 112, 1.012 with 16;
+  // 8 GPUs: 0.973 vs 0.999 with 56, 1.000 with 16).
+  const int64_t dflt = (world <= 2) ? 128 : 32;
+  c.max_blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(max_blocks > 0 ? max_blocks : dflt, slot_blocks), kNumSMs)));
   for (auto& e : h->ar_ev) if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   return 0;
 }
@@ -1177,12 +1182,22 @@ int mfvae_allreduce_grads(MfvaeHandle h, int64_t begin, int64_t end, int32_t do_
   const int64_t e8 = round_up(end, 8);
   if (e8 <= begin) return 0;
   const CommCtx& c = h->comm;
+  // measurement switches (never set in production): MFVAE_DP_DEBUG=noar packs without reducing, =nosmall skips the tiny buckets'
+  // cross-rank kernel -- they locate the data-parallel overhead; results are then per-rank, not reduced
+  static const char* dbg = getenv("MFVAE_DP_DEBUG");
+  const bool noar = dbg && strstr(dbg, "noar"), nosmall = dbg && strstr(dbg, "nosmall");
+  if ((e8 - begin) * 4 <= c.small_bytes && nosmall) {
+    __nv_bfloat16* sh = static_cast<__nv_bfloat16*>(h->ar.d_shadow_bf16);
+    return do_adam ? launch_adam(h->ar.d_param + begin, h->ar.d_grad + begin, h->ar.d_m + begin, h->ar.d_v + begin, sh ? sh + begin : nullptr,
+                                 e8 - begin, lr, beta1, beta2, eps, t, s) : 0;
+  }
   if ((e8 - begin) * 4 <= c.small_bytes) {
     __nv_bfloat16* sh = static_cast<__nv_bfloat16*>(h->ar.d_shadow_bf16);
     return comm_small_allreduce_adam(c, e8 - begin, h->ar.d_param + begin, h->ar.d_grad + begin, h->ar.d_m + begin, h->ar.d_v + begin,
                                      sh ? sh + begin : nullptr, do_adam, lr, beta1, beta2, eps, t, s);
   }
-  MFVAE_TRY(comm_allreduce(c, begin, e8, s, h->ar.d_grad));       // pack (fp32 -> payload) + two-shot reduce, one kernel
+  if (noar) MFVAE_TRY(comm_pack(h->ar.d_grad, c.local, c.dtype, begin, e8, s));
+  else MFVAE_TRY(comm_allreduce(c, begin, e8, s, h->ar.d_grad));       // pack (fp32 -> payload) + two-shot reduce, one kernel
   if (do_adam) {
     // the optimizer sweep of this range runs on the handle's optimizer stream behind the reduce, so that the next bucket's
     // reduce (on `stream`) does not queue behind a 100-200 MB sweep; mfvae_opt_join makes the caller's stream wait for it
@@ -1211,6 +1226,7 @@ int mfvae_opt_join(MfvaeHandle h, void* stream) {
 // sum of the 4 loss scalars of the step in flight across ranks (in place in the handle's loss slots), on `stream`
 int mfvae_allreduce_losses(MfvaeHandle h, void* stream) {
   MFVAE_CHECK(h && h->comm.world >= 2 && h->ws, "comm: not bound");
+  { static const char* dbg = getenv("MFVAE_DP_DEBUG"); if (dbg && strstr(dbg, "noloss")) return 0; }
   return comm_allreduce_scalars(h->comm, losses_ptr(h), 4, losses_ptr(h), static_cast<cudaStream_t>(stream));
 }
 

@@ -794,7 +794,7 @@ class MAVAE(nn.Module):
         csp = C.c_void_p(cs.cuda_stream)
         if adam is not None:
             self._adam_t += 1
-        if self._native_comm and not _DP_DEBUG:
+        if self._native_comm and not any(k in _DP_DEBUG for k in ("nocomm", "lateloss")):
             # the library's own exchange kernels: per bucket pack -> two-shot reduce over peer memory -> Adam from the window
             lr, betas, eps = adam if adam is not None else (0.0, (0.9, 0.999), 1e-8)
             if not self._losses_reduced:

@@ -215,7 +215,7 @@ int mfvae_bucket_wait(MfvaeHandle h, int32_t i, void* stream);
  *   multicast_window multicast (NVLS) mapping of the same windows, or NULL -> plain peer loads / stores
  *   d_signal_pads    device array [world] of zero-initialised 32-bit flag pads of signal_pad_bytes each (slots [0, 64) are not used)
  * payload_bf16 = 1 ships gradients as bf16 (the switch / the reducing rank accumulates in fp32); 0 ships fp32.
- * Every rank must issue the same sequence of mfvae_allreduce_* calls.  max_blocks (0 = 128 at 2 ranks, 32 from 3 ranks: measured) caps the CTAs of a reduce; one 32-bit
+ * Every rank must issue the same sequence of mfvae_allreduce_* calls.  max_blocks (0 = 64 at 2 ranks, 32 from 3 ranks: measured) caps the CTAs of a reduce; one 32-bit
  * flag per (CTA, peer) is used behind the first 64 slots of a pad, so signal_pad_bytes bounds it too. */
 int mfvae_comm_bind(MfvaeHandle h, int32_t rank, int32_t world, void* const* d_peer_windows, void* multicast_window,
                     void* const* d_signal_pads, int64_t signal_pad_bytes, void* local_window, int64_t window_bytes, int32_t payload_bf16,

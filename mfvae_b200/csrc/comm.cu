@@ -127,7 +127,8 @@ struct CommArgs {
 // (Capping this kernel at 40 registers so that it fits beside three resident GEMM CTAs of backward's small layers was measured:
 // no change at 2 GPUs -- the data-parallel overhead is not CTA eviction.)
 template <typename TP, bool MC>
-__global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommArgs c, int64_t byte0, int64_t byte1, const float* __restrict__ src) {
+__global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommArgs c, int64_t byte0, int64_t byte1, const float* __restrict__ src,
+                                                                 int barriers) {
   if (src) {
     TP* w = reinterpret_cast<TP*>(static_cast<char*>(c.peers[c.rank]) + byte0);
     const int64_t n4 = (byte1 - byte0) / (4 * static_cast<int64_t>(sizeof(TP)));
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommArgs c, int
       for (int u = 0; u < UP; ++u) if (i + u * pstride < n4) store4<TP>(w + (i + u * pstride) * 4, v[u]);
     }
   }
-  rank_barrier(c.pads, c.rank, c.world);                       // every rank's pack of this range has landed
+  if (barriers & 1) rank_barrier(c.pads, c.rank, c.world);     // every rank's pack of this range has landed
   const int64_t nvec = (byte1 - byte0) >> 4;
   const int64_t per = (nvec + c.world - 1) / c.world;
   const int64_t v0 = min(nvec, per * c.rank), v1 = min(nvec, v0 + per);
@@ -170,8 +171,12 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommArgs c, int
       }
     }
   }
-  rank_barrier(c.pads, c.rank, c.world);                       // every slice has been written into every window
+  if (barriers & 2) rank_barrier(c.pads, c.rank, c.world);     // every slice has been written into every window
 }
+
+// the cross-rank meeting as its own one-warp kernel: between a wide pack and a wide reduce it keeps the waiting (rank skew:
+// tens of microseconds) out of kernels whose resident CTAs would take slots from backward's GEMMs while they spin
+__global__ void __launch_bounds__(32) rendezvous_kernel(CommArgs c) { rank_barrier(c.pads, c.rank, c.world); }
 
 // one-shot all-reduce of a few fp32 scalars (the loss partials): every rank reduces all of them into its own `out`
 template <bool MC>
@@ -296,6 +301,15 @@ int comm_unpack(const void* window, int dtype, float* g, int64_t begin, int64_t 
 }
 
 int comm_allreduce(const CommCtx& c, int64_t begin, int64_t end, cudaStream_t s, const float* pack_from) {
+  if (c.split_sync && pack_from) {
+    // pack (wide, no waiting) -> rendezvous (one warp) -> reduce (wide, no waiting) -> rendezvous (one warp)
+    MFVAE_TRY(comm_pack(pack_from, c.local, c.dtype, begin, end, s));
+    CommArgs a0{c.rank, c.world, c.d_peers, static_cast<char*>(c.mc), c.d_pads};
+    rendezvous_kernel<<<1, 32, 0, s>>>(a0);
+    MFVAE_LAUNCH_CHECK();
+    pack_from = nullptr;
+  }
+  const int barriers = c.split_sync ? 0 : 3;
   MFVAE_CHECK(begin % 8 == 0 && end % 8 == 0 && end >= begin, "comm: ranges must be 8-element aligned");
   if (end == begin) return 0;
   const int64_t es = (c.dtype == kBF16) ? 2 : 4;
@@ -306,13 +320,14 @@ int comm_allreduce(const CommCtx& c, int64_t begin, int64_t end, cudaStream_t s,
   const int64_t nvec = (b1 - b0) / 16;
   const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(c.max_blocks, (nvec + kCommThreads * 8 - 1) / (kCommThreads * 8))));
   if (c.dtype == kBF16) {
-    if (c.mc) allreduce_kernel<__nv_bfloat16, true><<<blocks, kCommThreads, 0, s>>>(a, b0, b1, src);
-    else      allreduce_kernel<__nv_bfloat16, false><<<blocks, kCommThreads, 0, s>>>(a, b0, b1, src);
+    if (c.mc) allreduce_kernel<__nv_bfloat16, true><<<blocks, kCommThreads, 0, s>>>(a, b0, b1, src, barriers);
+    else      allreduce_kernel<__nv_bfloat16, false><<<blocks, kCommThreads, 0, s>>>(a, b0, b1, src, barriers);
   } else {
-    if (c.mc) allreduce_kernel<float, true><<<blocks, kCommThreads, 0, s>>>(a, b0, b1, src);
-    else      allreduce_kernel<float, false><<<blocks, kCommThreads, 0, s>>>(a, b0, b1, src);
+    if (c.mc) allreduce_kernel<float, true><<<blocks, kCommThreads, 0, s>>>(a, b0, b1, src, barriers);
+    else      allreduce_kernel<float, false><<<blocks, kCommThreads, 0, s>>>(a, b0, b1, src, barriers);
   }
   MFVAE_LAUNCH_CHECK();
+  if (c.split_sync) { rendezvous_kernel<<<1, 32, 0, s>>>(a); MFVAE_LAUNCH_CHECK(); }
   return 0;
 }
 

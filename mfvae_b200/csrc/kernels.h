@@ -106,6 +106,7 @@ struct CommCtx {
   int64_t scalar_off = 0;              // byte offset of a 256-byte fp32 scalar region behind it
   int64_t small_off = 0, small_bytes = 0;   // fp32 scratch for tiny ranges reduced by one single-CTA kernel
   int max_blocks = 16;
+  int split_sync = 0;                  // 1: pack / rendezvous / reduce / rendezvous as four launches (no wide kernel ever waits for a peer)
 };
 int comm_pack(const float* g, void* window, int dtype, int64_t begin, int64_t end, cudaStream_t s);
 int comm_unpack(const void* window, int dtype, float* g, int64_t begin, int64_t end, cudaStream_t s);

@@ -1162,8 +1162,12 @@ int mfvae_comm_bind(MfvaeHandle h, int32_t rank, int32_t world, void* const* d_p
   // flight: 128 CTAs (0.985 ms vs 1.04 with 32).  From 4 GPUs the slices are small and the reduce mostly waits in its barriers,
   // where resident CTAs only take slots from backward's kernels: 32 CTAs (4 GPUs: 0.956 vs 0.997 with 112, 1.012 with 16;
   // 8 GPUs: 0.973 vs 0.999 with 56, 1.000 with 16).
-  const int64_t dflt = (world <= 2) ? 128 : 32;
+  // (with the split synchronisation 64 CTAs do at 2 ranks what took 128 with the barriers inside: 0.955 vs 0.969 ms)
+  const int64_t dflt = (world <= 2) ? 64 : 32;
   c.max_blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(max_blocks > 0 ? max_blocks : dflt, slot_blocks), kNumSMs)));
+  // default: pack / rendezvous / reduce / rendezvous as four launches -- no wide kernel ever waits for a peer (4 GPUs: 0.953 ->
+  // 0.919 ms against the single kernel with barriers inside); MFVAE_DP_SPLIT_SYNC=0 selects the single kernel
+  { const char* e = getenv("MFVAE_DP_SPLIT_SYNC"); c.split_sync = (e && e[0] == '0') ? 0 : 1; }
   for (auto& e : h->ar_ev) if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   return 0;
 }

@@ -188,6 +188,13 @@ int mfvae_set_sm_reserve(MfvaeHandle h, int32_t n_sms);
  * (d_recon_r, d_latent and d_losses are valid); call mfvae_forward when recon_s itself is wanted. */
 int mfvae_fwd_bwd(MfvaeHandle h, const MfvaeBatch* b, MfvaeOutputs* out, void* stream);
 
+/* ONE call = one train step: mfvae_fwd_bwd, then -- when mfvae_comm_bind has been called -- the data-parallel exchange of
+ * every gradient bucket on the library's own communication stream with the bucket's Adam behind it, else the overlapped
+ * single-GPU Adam.  t = 1-based optimizer step; pipeline = 1: do not order `stream` behind the decoder block's optimizer sweep
+ * (mfvae_opt_join).  Equivalent to the call-by-call sequence of INTEGRATION.md section 4. */
+int mfvae_train_step(MfvaeHandle h, const MfvaeBatch* b, float lr, float beta1, float beta2, float eps, int64_t t, int32_t pipeline,
+                     MfvaeOutputs* out, void* stream);
+
 /* instrumentation: number of kernels this library has launched so far (process-wide), and optional CUDA-event
  * timing of every GEMM launch of the step on its launching stream.  With profiling on, each step records
  * start/stop events around its GEMM launches; mfvae_profile_read synchronises and returns, per GEMM of the last

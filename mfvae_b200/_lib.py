@@ -83,6 +83,7 @@ SIGNATURES = {
     "mfvae_bucket_read_wait": (C.c_int, [_vp, _i32, _vp]),
     "mfvae_set_sm_reserve": (C.c_int, [_vp, _i32]),
     "mfvae_fwd_bwd": (C.c_int, [_vp, C.POINTER(MfvaeBatch), C.POINTER(MfvaeOutputs), _vp]),
+    "mfvae_train_step": (C.c_int, [_vp, C.POINTER(MfvaeBatch), _f, _f, _f, _f, _i64, _i32, C.POINTER(MfvaeOutputs), _vp]),
     "mfvae_launch_count": (C.c_uint64, []),
     "mfvae_profile_enable": (C.c_int, [_vp, _i32]),
     "mfvae_profile_read": (_i32, [_vp, C.POINTER(MfvaeGemmTiming), _i32]),

@@ -111,6 +111,7 @@ struct MfvaeHandle_ {
   cudaEvent_t enc_prof_ev[2] = {nullptr, nullptr}; bool enc_prof_hit = false;   // the fused encoder chain, timed as one item
 
   std::vector<cudaEvent_t> ar_ev = std::vector<cudaEvent_t>(8, nullptr); size_t ar_ev_i = 0;   // reduce -> optimizer-stream hand-off
+  cudaStream_t comm_stream = nullptr; cudaEvent_t comm_done_ev = nullptr;   // mfvae_train_step's own communication stream
   CommCtx comm;                              // data-parallel exchange over peer memory (mfvae_comm_bind); world == 1: unbound
   // gradient buckets (arena ranges) and their completion events
   struct Bucket { int64_t begin, end; cudaEvent_t ev; };
@@ -945,6 +946,8 @@ int mfvae_destroy(MfvaeHandle h) {
   for (cudaEvent_t e : {h->aux_fork_ev, h->aux_join_ev, h->aux_fork2_ev, h->aux_join2_ev}) if (e) cudaEventDestroy(e);
   if (h->eb_ev) cudaEventDestroy(h->eb_ev);
   for (auto e : h->ar_ev) if (e) cudaEventDestroy(e);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->comm_done_ev) cudaEventDestroy(h->comm_done_ev);
   if (h->opt_ev) cudaEventDestroy(h->opt_ev);
   if (h->dec_read_ev) cudaEventDestroy(h->dec_read_ev);
   for (int i = 0; i < 3; ++i) if (h->read_ev[i]) cudaEventDestroy(h->read_ev[i]);
@@ -1232,6 +1235,39 @@ int mfvae_allreduce_losses(MfvaeHandle h, void* stream) {
   MFVAE_CHECK(h && h->comm.world >= 2 && h->ws, "comm: not bound");
   { static const char* dbg = getenv("MFVAE_DP_DEBUG"); if (dbg && strstr(dbg, "noloss")) return 0; }
   return comm_allreduce_scalars(h->comm, losses_ptr(h), 4, losses_ptr(h), static_cast<cudaStream_t>(stream));
+}
+
+// One call = one train step (SURVEY 8b `mfvae_train_step`): forward + ELBO + backward, the data-parallel exchange when
+// mfvae_comm_bind has been called (per bucket, on the library's own high-priority communication stream, behind that bucket's
+// events), and Adam (per bucket, overlapped with the rest of backward).  `t` is the 1-based optimizer step.  pipeline = 1
+// returns without ordering `stream` behind the decoder block's optimizer sweep (see mfvae_opt_join).  This is the sequence the
+// Python host issues call by call (mfvae_b200/model.py::train_step); a C host gets it in one.
+int mfvae_train_step(MfvaeHandle h, const MfvaeBatch* b, float lr, float beta1, float beta2, float eps, int64_t t, int32_t pipeline,
+                     MfvaeOutputs* out, void* stream) {
+  MFVAE_CHECK(h && b, "null handle or batch");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MFVAE_TRY(mfvae_fwd_bwd(h, b, out, stream));
+  if (h->comm.world < 2) return mfvae_adam_step_overlapped(h, lr, beta1, beta2, eps, t, stream);
+  if (!h->comm_stream) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    MFVAE_CUDA(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, hi));
+    MFVAE_CUDA(cudaEventCreateWithFlags(&h->comm_done_ev, cudaEventDisableTiming));
+  }
+  cudaStream_t cs = h->comm_stream;
+  MFVAE_TRY(mfvae_loss_wait(h, cs));
+  MFVAE_TRY(mfvae_allreduce_losses(h, cs));
+  for (int32_t i = 0; i < static_cast<int32_t>(h->buckets.size()); ++i) {
+    const int64_t bb = h->buckets[i].begin, be = std::min(h->buckets[i].end, h->optimized_elems);
+    if (be <= bb) continue;
+    MFVAE_TRY(mfvae_bucket_wait(h, i, cs));
+    MFVAE_TRY(mfvae_bucket_read_wait(h, i, cs));
+    MFVAE_TRY(mfvae_allreduce_grads(h, bb, be, 1, lr, beta1, beta2, eps, t, cs));
+  }
+  MFVAE_CUDA(cudaEventRecord(h->comm_done_ev, cs));
+  MFVAE_CUDA(cudaStreamWaitEvent(s, h->comm_done_ev, 0));
+  if (!pipeline) MFVAE_TRY(mfvae_opt_join(h, stream));
+  return 0;
 }
 
 uint64_t mfvae_launch_count(void) { return g_launch_count; }

@@ -868,6 +868,28 @@ class MAVAE(nn.Module):
             dist.all_reduce(self._losses, group=self._pg)
         return self._losses
 
+    def train_step_c(self, pb: PackedBatch, lr: float, betas=(0.9, 0.999), eps=1e-8, loss_weights=None, pipeline=False):
+        """``train_step`` through the single C entry ``mfvae_train_step`` (what a C host calls: the exchange runs on the
+        library's own communication stream).  Same results as ``train_step``; data parallel needs the native exchange."""
+        self._require_gpu()
+        if self.data_parallel and not self._native_comm:
+            raise RuntimeError("mfvae_b200: mfvae_train_step needs the native exchange (MFVAE_DP_COMM=native)")
+        lib = L.lib()
+        self._bind(pb.batch)
+        self._sync_shadow()
+        self._set_weights(loss_weights)
+        self._serial += 1
+        self._grads_pending = self._losses_reduced = False
+        self._cur, self._cb = pb, self._cbatch(pb)
+        out = L.MfvaeOutputs()
+        self._adam_t += 1
+        L.check(lib.mfvae_train_step(self._h, C.byref(self._cb), float(lr), float(betas[0]), float(betas[1]), float(eps), self._adam_t,
+                                     int(bool(pipeline)), C.byref(out), self._stream()))
+        self._losses = self._ws_view(out.d_losses, 1, 4, 4)[0]
+        self.philox_step += 1
+        self._opt_pending = bool(pipeline and self.data_parallel)
+        return self._losses
+
     def train_step(self, pb: PackedBatch, lr: float, betas=(0.9, 0.999), eps=1e-8, loss_weights=None, pipeline=False):
         """Fast path: forward + fused ELBO + backward (+ all-reduce) + Adam, no autograd graph.
         Returns the device tensor [loss, s_loss, r_loss, kl_loss].  ``loss_weights`` = (kl_weight, r_weight[, s_weight])

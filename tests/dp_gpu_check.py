@@ -103,6 +103,16 @@ def main(precision):
             out[f"dropin_{route}_grad_rel_max"] = max(gr.values())
             if route == "fused":
                 out["dropin_fused_loss_rel"] = abs(lv_dp - lv_ref) / max(abs(lv_ref), 1e-30)
+    # the single C entry (mfvae_train_step: exchange on the library's own communication stream) against the call-by-call step
+    m2 = make(); m2.enable_data_parallel()
+    m3 = make(); m3.enable_data_parallel()
+    for step in range(2):
+        l2 = m2.train_step(batch(rank * Bl, (rank + 1) * Bl, rank * Bl), 1e-3).clone()
+        l3 = m3.train_step_c(batch(rank * Bl, (rank + 1) * Bl, rank * Bl), 1e-3).clone()
+    torch.cuda.synchronize()
+    if rank == 0:
+        out["single_call_loss_rel"] = max(abs(float(x) - float(y)) / max(abs(float(y)), 1e-30) for x, y in zip(l3, l2))
+        out["single_call_param_rel"] = rel(m3._arena[:m3._n_opt], m2._arena[:m2._n_opt])
     if rank == 0:
         print("DP_CHECK " + json.dumps(out), flush=True)
     # every rank must hold identical parameters after the step

@@ -30,6 +30,8 @@ def test_dp2_matches_single_gpu(precision):
     o = lines["DP_CHECK"]
     print(json.dumps(o))
     assert lines["DP_SYNC"]["identical_params_on_all_ranks"]
+    # one C call per step (mfvae_train_step) == the host's call-by-call sequence
+    assert o["single_call_loss_rel"] < (1e-6 if precision == "fp32" else 1e-3) and o["single_call_param_rel"] < (1e-6 if precision == "fp32" else 1e-2), o
     if precision == "fp32":
         assert o["loss_rel"] < 1e-5 and o["grad_rel_max"] < 1e-5 and o["param_rel_max"] < 1e-5, o
         # drop-in call sequence under data parallel: fused ELBO (global means) and torch loss over the autograd bridge

@@ -90,11 +90,19 @@ def create_dataset(transition, codebook):
 class HostStager:
     """Pinned-host staging ring: a sampled transition dict is packed once into page-locked memory and shipped
     with ONE asynchronous H2D copy (the reference issues 44 small ``.to(device)`` copies per step,
-    model.py:140,146 and :20-23).  ``depth`` slots let packing of batch k+1 overlap the copy of batch k."""
+    model.py:140,146 and :20-23).  ``depth`` slots let packing of batch k+1 overlap the copy of batch k.
 
-    def __init__(self, device, depth: int = 2):
+    ``obs_dtype=torch.bfloat16`` keeps the observation block in bf16 on the host (rows ``[obs bf16 | act | next | rew fp32]``,
+    25 % fewer PCIe bytes): the bf16 engine rounds observations on arrival anyway, so the train step is bit-identical to
+    shipping fp32 (``tests/test_gpu_frontends.py::test_bf16_observation_feed_is_bit_identical``); this is the row format
+    ``bench.py``'s ``e2e`` figure is measured on.  Reconstruction targets always travel in fp32."""
+
+    def __init__(self, device, depth: int = 2, obs_dtype=torch.float32):
+        if obs_dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("HostStager: obs_dtype must be torch.float32 or torch.bfloat16")
         self.device = torch.device(device)
         self.depth = depth
+        self.obs_dtype = obs_dtype
         self._host = [None] * depth
         self._dev = [None] * depth
         self._ev = [None] * depth
@@ -104,22 +112,49 @@ class HostStager:
     def stage(self, transition, codebook, sample0=0, batch_global=None) -> PackedBatch:
         agents, B, _, S, A = _layout(transition, codebook)
         W = int(sum(_act_dims(transition, agents)))
-        n = B * (2 * S + W + A)
         k = self._i
         self._i = (k + 1) % self.depth
         cuda = self.device.type == "cuda"
-        if self._host[k] is None or self._host[k].numel() != n:
-            self._host[k] = torch.empty(n, dtype=torch.float32, pin_memory=cuda)
-            self._dev[k] = torch.empty(n, dtype=torch.float32, device=self.device)
-        elif self._ev[k] is not None:
-            self._ev[k].synchronize()              # the previous copy out of this slot must have finished
-        _pack_numpy(transition, codebook, flat=self._host[k].numpy())
-        self._dev[k].copy_(self._host[k], non_blocking=True)
-        self.h2d_bytes = n * 4
+        if self.obs_dtype == torch.float32:
+            n = B * (2 * S + W + A)
+            if self._host[k] is None or self._host[k].numel() != n:
+                self._host[k] = torch.empty(n, dtype=torch.float32, pin_memory=cuda)
+                self._dev[k] = torch.empty(n, dtype=torch.float32, device=self.device)
+            elif self._ev[k] is not None:
+                self._ev[k].synchronize()              # the previous copy out of this slot must have finished
+            _pack_numpy(transition, codebook, flat=self._host[k].numpy())
+            self._dev[k].copy_(self._host[k], non_blocking=True)
+            self.h2d_bytes = n * 4
+            obs, act, nxt, rew = _split_flat(self._dev[k], B, S, A, W)
+        else:
+            # byte buffer: [obs bf16 (B*S*2, padded to 16) | act, next, rew fp32]; fp32 rows are packed first, then the
+            # observation block is rounded to bf16 in place on the host (one pass over B*S values)
+            ob = (B * S * 2 + 15) // 16 * 16
+            n32 = B * (S + W + A)
+            total = ob + n32 * 4
+            if self._host[k] is None or self._host[k].numel() != total:
+                self._host[k] = torch.empty(total, dtype=torch.uint8, pin_memory=cuda)
+                self._dev[k] = torch.empty(total, dtype=torch.uint8, device=self.device)
+                self._scratch = torch.empty(B * (2 * S + W + A), dtype=torch.float32)
+            elif self._ev[k] is not None:
+                self._ev[k].synchronize()
+            _pack_numpy(transition, codebook, flat=self._scratch.numpy())
+            so, sa, sn, sr = _split_flat(self._scratch, B, S, A, W)
+            h = self._host[k]
+            h[:B * S * 2].view(torch.bfloat16).view(B, S).copy_(so)
+            tail = h[ob:].view(torch.float32)
+            tail[:B * W].view(B, W).copy_(sa)
+            tail[B * W:B * (W + S)].view(B, S).copy_(sn)
+            tail[B * (W + S):].view(B, A).copy_(sr)
+            self._dev[k].copy_(h, non_blocking=True)
+            self.h2d_bytes = total
+            d = self._dev[k]
+            dt = d[ob:].view(torch.float32)
+            obs = d[:B * S * 2].view(torch.bfloat16).view(B, S)
+            act, nxt, rew = dt[:B * W].view(B, W), dt[B * W:B * (W + S)].view(B, S), dt[B * (W + S):].view(B, A)
         if cuda:
             self._ev[k] = torch.cuda.Event()
             self._ev[k].record()
-        obs, act, nxt, rew = _split_flat(self._dev[k], B, S, A, W)
         return PackedBatch(obs, act, nxt, rew, sample0=sample0, batch_global=batch_global)
 
 

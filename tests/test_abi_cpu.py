@@ -112,6 +112,23 @@ def test_host_stager_cpu(built):
     assert pb.obs.shape == (6, spec.state_dim) and pb.act.shape == (6, 3)
 
 
+def test_host_stager_bf16_observation_rows(built):
+    """HostStager(obs_dtype=bfloat16): rows [obs bf16 | act | next | rew fp32] -- the e2e row format of bench.py; observations
+    are the bf16 rounding of the fp32 values, everything else is untouched, 25 % fewer bytes cross PCIe."""
+    spec = O.tiny_spec(3)
+    t = O.synth_transition(spec, 6, seed=5)
+    cb = {a: i for i, a in enumerate(spec.agents)}
+    st32, st16 = built.HostStager("cpu"), built.HostStager("cpu", obs_dtype=torch.bfloat16)
+    a, b = st32.stage(t, cb), st16.stage(t, cb)
+    assert b.obs.dtype == torch.bfloat16 and torch.equal(b.obs, a.obs.to(torch.bfloat16))
+    assert torch.equal(b.act, a.act) and torch.equal(b.next, a.next) and torch.equal(b.rew, a.rew)
+    assert st16.h2d_bytes < st32.h2d_bytes and b.obs.is_contiguous() and b.next.is_contiguous()
+    b2 = st16.stage(t, cb); b3 = st16.stage(t, cb)          # ring slots are reused
+    assert torch.equal(b3.obs, b.obs) and torch.equal(b2.next, a.next)
+    with pytest.raises(TypeError):
+        built.HostStager("cpu", obs_dtype=torch.float16)
+
+
 def test_trainer_surface(built):
     spec = O.tiny_spec(3, idx_features=16, latent=8, act_features=8)
     m = built.MAVAE(16, 8, 8, True, spec.agents, spec.obs_dim, spec.n_act, "cpu", precision="fp32")

@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, in
   }
 }
 
+static int kColsumPerSm = 4;
 template <typename T>
 static int colsum_dispatch(const T* x, int G, int64_t B, int N, int64_t ld, int64_t gs, float* out, int64_t out_gs, cudaStream_t s) {
   // columns are read 4 at a time: the padded row (ld, a multiple of 8) always holds whole strips
@@ -492,7 +493,8 @@ static int colsum_dispatch(const T* x, int G, int64_t B, int N, int64_t ld, int6
   const int lpr = strips >= 32 ? 32 : (strips > 8 ? 16 : 8);
   const int ctiles = (strips + lpr - 1) / lpr;
   const int rpb = 256 / lpr;
-  const int64_t want = (static_cast<int64_t>(kNumSMs) * 4) / std::max<int64_t>(1, static_cast<int64_t>(ctiles) * G);
+  // (two CTAs per SM instead of four, to leave thread slots to the GEMMs they run beside, was measured: 0.823 -> 0.839 ms)
+  const int64_t want = (static_cast<int64_t>(kNumSMs) * kColsumPerSm) / std::max<int64_t>(1, static_cast<int64_t>(ctiles) * G);
   const int splits = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, (B + 4 * rpb - 1) / (4 * rpb))));
   dim3 grid(ctiles, splits, G);
   if (lpr == 32) colsum_kernel<T, 32><<<grid, 256, 0, s>>>(x, B, N, ld, gs, out, out_gs);

@@ -1088,7 +1088,7 @@ int mfvae_adam_step_overlapped(MfvaeHandle h, float lr, float beta1, float beta2
   __nv_bfloat16* sh = static_cast<__nv_bfloat16*>(h->ar.d_shadow_bf16);
   auto range = [&](int64_t b, int64_t e, cudaStream_t st) -> int {
     if (e <= b) return 0;
-    // 4 blocks per SM when it runs beside the wgrad tail: 8 x 256 threads would take every thread slot of the SM
+    // 4 blocks per SM when it runs beside the wgrad tail: 8 x 256 threads would take every thread slot of the SM (2 was measured too: slower)
     return launch_adam(h->ar.d_param + b, h->ar.d_grad + b, h->ar.d_m + b, h->ar.d_v + b, sh ? sh + b : nullptr, e - b,
                        lr, beta1, beta2, eps, t, st, st == s ? 8 : 4);
   };

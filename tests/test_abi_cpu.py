@@ -211,6 +211,27 @@ def test_launch_list_parser_on_committed_profile():
     assert "launches in step 59" in out.stdout
 
 
+def test_r2_launch_list_summary_matches_the_committed_profile(tmp_path):
+    """tools/summarize_launches.py reproduces profiles/r2_traffic.json (bench.py's roofline.traffic) from the committed ncu list."""
+    import json
+    import shutil
+    import subprocess
+    import sys
+    want = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+    keep = {f: open(os.path.join(ROOT, "profiles", f)).read() for f in ("r2_traffic.json", "r2_ncu_step_summary.txt")}
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "summarize_launches.py"),
+                              os.path.join(ROOT, "profiles", "r2_launches_cfg2_b4096.csv"), "r2"], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        got = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        assert got["cfg2_b4096"] == want["cfg2_b4096"]
+        assert got["cfg2_b4096"]["tensor_core_kernels_all_launches"]["launches"] == 33
+        assert got["cfg2_b4096"]["whole_step"]["launches"] == 58
+    finally:
+        for f, txt in keep.items():
+            open(os.path.join(ROOT, "profiles", f), "w").write(txt)
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys; under
     torchrun every rank but 0 exits 0 without work."""
